@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""Benchmark of the statevector -> reduced rho -> Wigner grid hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2]
+
+One "step" is one pass of the hot path over one batch of synthetic input: for the default config
+(BASELINE.json configs[1], "c2": 1 qubit + 2 qumodes at cutoff 64, trace to qumode 0, 1024 x 1024
+Wigner grid) that is  psi (8192 amplitudes) -> rho (64 x 64) -> W (1024 x 1024 float64).
+
+Under torchrun (N > 1) every rank runs the same per-rank workload (weak scaling: the frames of a
+batch are independent and are sharded across ranks), then the finished grids are gathered on rank 0
+over NCCL inside the timed step.  Rank 0 prints ONE JSON line.
+
+  value     whole-job Wigner grid points / s, inputs resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public NumPy API (C-ABI `_host` entry point): pinned host psi
+            -> H2D -> kernels -> D2H -> host W inside the timed region (wall clock)
+  roofline  dominant kernel (the Wigner Clenshaw kernel): algorithmic fp64 flops / its own event
+            time, against an fp64-FMA peak MEASURED on this GPU in the same run (MEASURED_PEAKS.json
+            has no fp64 entry); the HBM store side is reported next to it against hbm_gbs
+  cpu_baseline  the NumPy oracle (restatement of qutip/qiskit, oracle/) on a bounded sample, 1 thread
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import workloads  # noqa: E402
+
+METRIC = "wigner_grid_points_per_s_fp64"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--frames", type=int, default=None, help="frames per rank (c3)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="leave results sharded (skip the NCCL gather)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+def make_workload(name: str, world: int, frames: int | None) -> dict:
+    if name == "c3":
+        wl = workloads.config3(frames=frames or 64)
+    elif name == "c5":
+        wl = workloads.config5()
+    else:
+        wl = workloads.CONFIGS[name]()
+    return wl
+
+
+def describe(wl: dict, world: int) -> dict:
+    S = len(wl["xvec"])
+    frames = wl["psi"].shape[0] * (len(wl["traced_sets"]) if "traced_sets" in wl else 1)
+    return {
+        "workload": {
+            "c1": "c1: 1 qumode cutoff 16 + 1 qubit, displaced cat alpha=2, 200x200 grid",
+            "c2": "c2: 1 qubit + 2 qumodes cutoff 64, cond. displacement + beamsplitter, trace to qumode 0, Wigner 1024x1024",
+            "c3": "c3: Jaynes-Cummings frames cutoff 32 + 1 qubit, 400x400 Wigner per frame",
+            "c4": "c4: 4 sites cutoff 16, per-site reduced rho (batched partial trace) + Wigner 512x512 each",
+            "c5": "c5: single qumode cutoff 1024, Wigner 4096x4096",
+        }[wl["name"]],
+        "cutoff": int(wl["N"]),
+        "grid": [S, S],
+        "frames_per_gpu": int(frames),
+        "global_frames": int(frames * world),
+        "sharding": "frames" if world > 1 else "none",
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # under load = samples in the upper half of the power range
+        thr = 0.5 * (min(power) + max(power))
+        loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(power)), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(wl: dict, seconds: float):
+    """Times the NumPy oracle on a bounded row sample of the workload; returns (points/s, description)."""
+    from oracle import partial_trace_sv, wigner_clenshaw
+
+    psi = wl["psi"][0]
+    traced = wl["traced_sets"][0] if "traced_sets" in wl else wl["traced"]
+    x = wl["xvec"]
+    S = len(x)
+    N = wl["N"]
+    # NumPy cost model from SURVEY 6: ~1 algorithmic GFLOP/s -> rows that fit in `seconds`
+    per_row = S * workloads.flops_per_point(N) / 0.9e9
+    rows = int(max(1, min(S, seconds / per_row)))
+    ys = x[np.linspace(0, S - 1, rows).astype(int)]
+    t0 = time.perf_counter()
+    rho = partial_trace_sv(psi, traced)
+    W = wigner_clenshaw(rho, x, ys)
+    dt = time.perf_counter() - t0
+    assert W.shape == (rows, S)
+    return rows * S / dt, f"psi->rho->W on {rows} of {S} grid rows x {S} columns, 1 frame, {dt:.1f} s", rho, ys, W
+
+
+def _ref_worker(args):
+    rho, x, ys = args
+    from oracle import wigner_clenshaw
+
+    return wigner_clenshaw(rho, x, ys)
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU path (NumPy restatement; qutip/qiskit are not installed
+    anywhere this runs), fanned out over processes the way animate.py:191 fans frames out."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    from oracle import partial_trace_sv
+
+    wl = make_workload(args.config, world, args.frames)
+    cfg = describe(wl, world)
+    psi = wl["psi"][0]
+    traced = wl["traced_sets"][0] if "traced_sets" in wl else wl["traced"]
+    x = wl["xvec"]
+    S, N = len(x), wl["N"]
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    # per step: a row sample sized for ~ (cpu_seconds / steps) of wall time across all workers
+    budget = max(1.0, args.cpu_seconds * 4 / max(1, args.steps + args.warmup))
+    per_row = S * workloads.flops_per_point(N) / 0.9e9
+    rows = int(max(procs, min(S, budget * procs / per_row)))
+    rows -= rows % procs
+    ys = x[np.linspace(0, S - 1, rows).astype(int)]
+    chunks = np.array_split(ys, procs)
+    times = []
+    with mp.get_context("fork").Pool(procs) as pool:
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            rho = partial_trace_sv(psi, traced)
+            pool.map(_ref_worker, [(rho, x, c) for c in chunks])
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = rows * S / (ms * 1e-3)
+    sample = f"{rows} of {S} grid rows x {S} columns per step, {procs} worker processes (rows split evenly)"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from bosonic_qiskit_b200 import get_engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = get_engine(local)
+    wl = make_workload(args.config, world, args.frames)
+    cfg = describe(wl, world)
+    x_np = wl["xvec"]
+    S, N = len(x_np), int(wl["N"])
+    multi_sets = "traced_sets" in wl
+    frames = cfg["frames_per_gpu"]
+    points_rank = frames * S * S
+
+    psi_t = torch.from_numpy(wl["psi"]).to(dev)
+    x_t = torch.from_numpy(x_np).to(dev)
+    W_t = torch.empty((frames, S, S), dtype=torch.float64, device=dev)
+    rho_t = torch.empty((frames, N, N), dtype=torch.complex128, device=dev)
+    gathered = None
+    if world > 1 and not args.no_gather:
+        gathered = torch.empty((world * frames, S, S), dtype=torch.float64, device=dev) if rank == 0 else None
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        if multi_sets:
+            # c4: several traces of one psi, then one batched Wigner launch
+            import ctypes
+
+            from bosonic_qiskit_b200._lib import check
+            sets = wl["traced_sets"]
+            flat = (ctypes.c_int * (len(sets) * len(sets[0])))(*[q for s in sets for q in s])
+            check(eng._lib.bq_partial_trace_sv_multi_dev(eng._h, ctypes.c_void_p(psi_t.data_ptr()), wl["n_qubits"], flat,
+                                                         len(sets[0]), len(sets), ctypes.c_void_p(rho_t.data_ptr()),
+                                                         ctypes.c_void_p(stream.cuda_stream)))
+            eng.wigner_t(rho_t, x_t, out=W_t)
+        else:
+            eng.state_to_wigner_t(psi_t, wl["traced"], x_t, out=W_t, rho_out=rho_t)
+        if world > 1 and not args.no_gather:
+            if rank == 0:
+                dist.gather(W_t, list(gathered.view(world, frames, S, S).unbind(0)), dst=0)
+            else:
+                dist.gather(W_t, None, dst=0)
+
+    # ---- device-resident timing ------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    fp64_peak = eng.fp64_peak_tflops(1.0)  # sustained DFMA rate on this GPU, right before the timed region
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    eng.profile_read()
+    launches0 = eng.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for a, b in ev:
+        flush.fill_(1.0)  # L2 flush, outside the per-step events
+        a.record()
+        step_device()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = eng.launches - launches0
+    kern_ms, kern_n = eng.profile_read()
+    eng.profile(False)
+    total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = points_rank * world / (ms_per_step * 1e-3)
+
+    # ---- accuracy of what was just timed (rank 0, a row sample) ---------------------------------
+    # ---- end-to-end through the public NumPy API (host buffers) ---------------------------------
+    e2e = None
+    if not multi_sets:
+        psi_pin = eng.pinned_empty(wl["psi"].shape, np.complex128)
+        psi_pin[...] = wl["psi"]
+        out_pin = eng.pinned_empty((frames, S, S), np.float64)
+        for _ in range(3):
+            eng.state_to_wigner(psi_pin, wl["traced"], x_np, out=out_pin)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.state_to_wigner(psi_pin, wl["traced"], x_np, out=out_pin)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": points_rank * world * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(psi_pin.nbytes), "d2h_bytes_per_step": int(out_pin.nbytes),
+               "ms_per_step": 1e3 * dt / args.steps, "api": "Engine.state_to_wigner -> bq_state_to_wigner_host"}
+    else:
+        import bosonic_qiskit_b200  # noqa: F401
+
+        psi_np = wl["psi"][0]
+        for _ in range(3):
+            rhos = eng.partial_trace_sv_multi(psi_np, wl["traced_sets"])
+            eng.wigner(rhos, x_np)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rhos = eng.partial_trace_sv_multi(psi_np, wl["traced_sets"])
+            Wh = eng.wigner(rhos, x_np)
+        dt = time.perf_counter() - t0
+        e2e = {"value": points_rank * world * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(psi_np.nbytes + rhos.nbytes),
+               "d2h_bytes_per_step": int(Wh.nbytes + rhos.nbytes), "ms_per_step": 1e3 * dt / args.steps,
+               "api": "Engine.partial_trace_sv_multi + Engine.wigner (host entry points)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    F = workloads.flops_per_point(N)
+    kern_avg_ms = kern_ms / max(kern_n, 1)
+    achieved_tf = points_rank * F / (kern_avg_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "kernel": "wigner_resident_kernel" if N <= 64 else "wigner_stream_kernel",
+        "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+        "peak_source": "DFMA probe kernel run for 1 s on this GPU immediately before the timed region (bq_fp64_peak); "
+                       "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+        "flops_per_point": F, "points_per_launch": points_rank, "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
+        "kernel_share_of_step": kern_avg_ms / ms_per_step,
+        "traffic": None,
+        "hbm_store": {"bound": "hbm", "achieved": points_rank * 8 / (kern_avg_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                      "unit": "GB/s", "peak_source": hbm_src,
+                      "frac": points_rank * 8 / (kern_avg_ms * 1e-3) / 1e9 / hbm_peak},
+    }
+
+    # parity of the timed output against the oracle (row sample) and the CPU baseline, same inputs
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline and world == 1:
+        v, sample, rho_ref, ys, W_ref = cpu_sample(wl, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": sample + " (NumPy restatement of qiskit.partial_trace + qutip.wigner clenshaw; "
+                                  "qutip/qiskit are not installed)"}
+        idx = np.linspace(0, S - 1, len(ys)).astype(int)
+        W_dev = W_t[0].cpu().numpy()[idx]
+        rho_dev = rho_t[0].cpu().numpy()
+        parity = {"max_abs_dW_over_max_W": float(np.abs(W_dev - W_ref).max() / np.abs(W_ref).max()),
+                  "max_abs_drho_over_max_rho": float(np.abs(rho_dev - rho_ref).max() / np.abs(rho_ref).max()),
+                  "tolerance": 1e-10}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+        "gather": None if world == 1 else ("nccl gather to rank 0 inside the step" if not args.no_gather else "none (sharded)"),
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,859 @@
+// C ABI of the library (include/bq_b200.h): argument checking, per-device workspaces, host <-> device
+// staging for the `_host` entry points, and the orchestration psi -> rho -> coefficient stream -> W.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/bq_b200.h"
+#include "bq_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return BQ_ERR_CUDA;
+}
+#define CU(call)                                       \
+    do {                                               \
+        cudaError_t e__ = (call);                      \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+
+struct Buffer {  // grow-only device scratch
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t need)
+    {
+        if (need <= bytes) return cudaSuccess;
+        if (ptr) {
+            cudaError_t e = cudaFree(ptr);  // implicit device sync: nothing in flight still reads it
+            ptr = nullptr;
+            bytes = 0;
+            if (e != cudaSuccess) return e;
+        }
+        const size_t cap = std::max(need, (size_t)4096);
+        cudaError_t e = cudaMalloc(&ptr, cap);
+        if (e == cudaSuccess) bytes = cap;
+        return e;
+    }
+    void release()
+    {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        bytes = 0;
+    }
+};
+
+constexpr int kCtrSlots = 64;
+
+}  // namespace
+
+struct bq_handle_s {
+    bq::DeviceInfo dev;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;  // used by the _host entry points
+    cudaEvent_t ev_order = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+
+    std::map<int, double4 *> tabs;                          // cutoff -> constant table
+    std::map<std::vector<int>, bq::TraceMap *> maps;        // (n_qubits, n_traced, sets...) -> device maps
+    Buffer cs, partial, rho_tmp;                            // kernel scratch
+    Buffer in_dev, out_dev, rho_dev, grid_dev, small_dev;   // staging for _host calls
+    std::vector<double> grid_host;                          // what grid_dev currently holds
+    unsigned int *ctr = nullptr;
+    int ctr_next = 0;
+    uint64_t launches = 0;
+    double last_ms = 0.0;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// Scratch is shared by consecutive calls; if the caller hops streams, chain them.
+int order_stream(bq_handle_t h, cudaStream_t st)
+{
+    if (h->have_last && h->last_stream != st) {
+        CU(cudaEventRecord(h->ev_order, h->last_stream));
+        CU(cudaStreamWaitEvent(st, h->ev_order, 0));
+    }
+    h->last_stream = st;
+    h->have_last = true;
+    return BQ_OK;
+}
+
+int get_tab(bq_handle_t h, int N, cudaStream_t st, const double4 **out)
+{
+    auto it = h->tabs.find(N);
+    if (it == h->tabs.end()) {
+        double4 *tab = nullptr;
+        CU(cudaMalloc(&tab, (size_t)bq::stream_records(N) * sizeof(double4)));
+        cudaError_t e = bq::launch_build_tab(tab, N, st);
+        if (e != cudaSuccess) {
+            cudaFree(tab);
+            return fail_cuda(e, "build_tab");
+        }
+        ++h->launches;
+        // later calls may come on another stream: make the table globally visible now
+        CU(cudaStreamSynchronize(st));
+        it = h->tabs.emplace(N, tab).first;
+    }
+    *out = it->second;
+    return BQ_OK;
+}
+
+int build_map(int n_qubits, const int *traced, int n_traced, bq::TraceMap *m)
+{
+    if (n_qubits < 0 || n_qubits > bq::kMaxQubits) return fail(BQ_ERR_INVALID, "n_qubits out of range [0, 40]");
+    if (n_traced < 0 || n_traced > n_qubits) return fail(BQ_ERR_INVALID, "n_traced out of range");
+    if (n_traced > 0 && !traced) return fail(BQ_ERR_INVALID, "traced is NULL");
+    bool is_tr[bq::kMaxQubits] = {};
+    for (int i = 0; i < n_traced; ++i) {
+        const int q = traced[i];
+        if (q < 0 || q >= n_qubits) return fail(BQ_ERR_INVALID, "traced qubit index out of range");
+        if (is_tr[q]) return fail(BQ_ERR_INVALID, "duplicate traced qubit index");
+        is_tr[q] = true;
+    }
+    std::memset(m, 0, sizeof(*m));
+    for (int q = 0; q < n_qubits; ++q) {
+        if (is_tr[q])
+            m->trace[m->n_trace++] = q;
+        else
+            m->keep[m->n_keep++] = q;
+    }
+    return BQ_OK;
+}
+
+int get_maps(bq_handle_t h, int n_qubits, const int *traced, int n_traced, int n_sets, const bq::TraceMap **out)
+{
+    std::vector<int> key;
+    key.reserve(3 + (size_t)n_traced * n_sets);
+    key.push_back(n_qubits);
+    key.push_back(n_traced);
+    key.push_back(n_sets);
+    for (int i = 0; i < n_traced * n_sets; ++i) key.push_back(traced[i]);
+    auto it = h->maps.find(key);
+    if (it == h->maps.end()) {
+        std::vector<bq::TraceMap> host((size_t)n_sets);
+        for (int s = 0; s < n_sets; ++s) {
+            int rc = build_map(n_qubits, traced ? traced + (size_t)s * n_traced : nullptr, n_traced, &host[s]);
+            if (rc) return rc;
+        }
+        if (h->maps.size() >= 512) {  // bounded cache
+            CU(cudaDeviceSynchronize());
+            for (auto &kv : h->maps) cudaFree(kv.second);
+            h->maps.clear();
+        }
+        bq::TraceMap *d = nullptr;
+        CU(cudaMalloc(&d, sizeof(bq::TraceMap) * n_sets));
+        cudaError_t e = cudaMemcpy(d, host.data(), sizeof(bq::TraceMap) * n_sets, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            return fail_cuda(e, "upload trace map");
+        }
+        it = h->maps.emplace(std::move(key), d).first;
+    }
+    *out = it->second;
+    return BQ_OK;
+}
+
+int check_method(int method)
+{
+    switch (method) {
+    case BQ_WIGNER_CLENSHAW:
+    case BQ_WIGNER_ITERATIVE:
+    case BQ_WIGNER_LAGUERRE:
+        return BQ_OK;
+    case BQ_WIGNER_FFT:
+        return fail(BQ_ERR_UNSUPPORTED, "method 'fft' is not implemented by the B200 path");
+    default:
+        return fail(BQ_ERR_INVALID, "method must be either 'iterative', 'laguerre', 'fft' or 'clenshaw'.");
+    }
+}
+
+// device-side core: rho (device) -> W (device)
+int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                const double *d_x, int nx, const double *d_y, int ny, double g, double *d_W, cudaStream_t st)
+{
+    if (batch == 0 || nx == 0 || ny == 0) return BQ_OK;
+    const double4 *tab = nullptr;
+    int rc = get_tab(h, N, st, &tab);
+    if (rc) return rc;
+    const int64_t R = bq::stream_records(N);
+    CU(h->cs.reserve((size_t)R * batch * sizeof(double2)));
+    int nl = 0;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = std::min(65535, batch - b0);
+        cudaError_t e = bq::launch_pack_rho(d_rho + (int64_t)b0 * rho_stride, ld, rho_stride, N, nb,
+                                            (double2 *)h->cs.ptr + (int64_t)b0 * R, R, st);
+        if (e != cudaSuccess) return fail_cuda(e, "pack_rho");
+        ++nl;
+    }
+    bq::WigParams p{};
+    p.cs = (const double2 *)h->cs.ptr;
+    p.tab = tab;
+    p.xvec = d_x;
+    p.yvec = d_y;
+    p.W = d_W;
+    p.w_stride = (int64_t)nx * ny;
+    p.cs_stride = R;
+    p.N = N;
+    p.R_tot = (int)R;
+    p.nx = nx;
+    p.ny = ny;
+    p.batch = batch;
+    p.g = g;
+    p.scale = g * g * 0.5 / 3.14159265358979323846;
+    p.ctr = h->ctr + 2 * h->ctr_next;
+    h->ctr_next = (h->ctr_next + 1) % kCtrSlots;
+    cudaEvent_t pa = nullptr, pb = nullptr;
+    if (h->profile) {
+        CU(cudaEventCreate(&pa));
+        CU(cudaEventCreate(&pb));
+        CU(cudaEventRecord(pa, st));
+    }
+    cudaError_t e = bq::launch_wigner(p, h->dev, st, &nl);
+    h->launches += nl;
+    if (h->profile) {
+        cudaEventRecord(pb, st);
+        h->prof_events.emplace_back(pa, pb);
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "launch_wigner");
+    return BQ_OK;
+}
+
+int check_wigner_args(const void *rho, int N, int64_t ld, int64_t rho_stride, int batch, const void *x, int nx,
+                      const void *y, int ny, double g, const void *W)
+{
+    if (N < 1 || N > 16384) return fail(BQ_ERR_INVALID, "cutoff N out of range [1, 16384]");
+    if (batch < 0 || nx < 0 || ny < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (ld < N) return fail(BQ_ERR_INVALID, "leading dimension smaller than N");
+    if (batch > 1 && rho_stride < 0) return fail(BQ_ERR_INVALID, "negative rho_stride");
+    if (!std::isfinite(g)) return fail(BQ_ERR_INVALID, "g is not finite");
+    if (batch > 0 && nx > 0 && ny > 0 && (!rho || !x || !y || !W)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    return BQ_OK;
+}
+
+// uploads (xvec, yvec) unless the device copy already holds exactly these values
+int stage_grid(bq_handle_t h, const double *x, int nx, const double *y, int ny, const double **dx, const double **dy)
+{
+    const size_t n = (size_t)nx + ny;
+    bool same = h->grid_host.size() == n + 2 && h->grid_host[0] == nx && h->grid_host[1] == ny &&
+                std::memcmp(h->grid_host.data() + 2, x, sizeof(double) * nx) == 0 &&
+                std::memcmp(h->grid_host.data() + 2 + nx, y, sizeof(double) * ny) == 0;
+    if (!same) {
+        CU(cudaStreamSynchronize(h->stream));
+        CU(h->grid_dev.reserve(sizeof(double) * std::max<size_t>(n, 1)));
+        h->grid_host.assign(n + 2, 0.0);
+        h->grid_host[0] = nx;
+        h->grid_host[1] = ny;
+        std::memcpy(h->grid_host.data() + 2, x, sizeof(double) * nx);
+        std::memcpy(h->grid_host.data() + 2 + nx, y, sizeof(double) * ny);
+        if (n) CU(cudaMemcpy(h->grid_dev.ptr, h->grid_host.data() + 2, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    *dx = (const double *)h->grid_dev.ptr;
+    *dy = (const double *)h->grid_dev.ptr + nx;
+    return BQ_OK;
+}
+
+int trace_sv_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced, int n_sets,
+                  int batch, int64_t psi_stride, double2 *d_rho, cudaStream_t st)
+{
+    const bq::TraceMap *maps = nullptr;
+    int rc = get_maps(h, n_qubits, traced, n_traced, n_sets, &maps);
+    if (rc) return rc;
+    const int n_keep = n_qubits - n_traced;
+    if (n_keep > 15) return fail(BQ_ERR_INVALID, "reduced density matrix larger than 2^15 x 2^15");
+    const int64_t D = (int64_t)1 << n_keep;
+    const int zmax = std::max(1, 65535 / n_sets);
+    for (int b0 = 0; b0 < batch; b0 += zmax) {
+        const int nb = std::min(zmax, batch - b0);
+        CU(h->partial.reserve(bq::trace_sv_scratch_bytes(n_keep, n_traced, nb, n_sets)));
+        int nl = 0;
+        // output layout [set][batch][D][D]: with several sets and a sliced batch the slices interleave,
+        // so slicing is only done for the single-set case (multi-set calls are batch == 1)
+        cudaError_t e = bq::launch_trace_sv(d_psi + (int64_t)b0 * psi_stride, psi_stride, nb, maps, n_sets, n_keep,
+                                            n_traced, d_rho + (int64_t)b0 * D * D, (double2 *)h->partial.ptr, h->dev,
+                                            st, &nl);
+        h->launches += nl;
+        if (e != cudaSuccess) return fail_cuda(e, "launch_trace_sv");
+    }
+    return BQ_OK;
+}
+
+int check_trace_args(const void *psi, int n_qubits, int n_traced, int batch, int64_t psi_stride, const void *out)
+{
+    if (n_qubits < 0 || n_qubits > bq::kMaxQubits) return fail(BQ_ERR_INVALID, "n_qubits out of range [0, 40]");
+    if (n_traced < 0 || n_traced > n_qubits) return fail(BQ_ERR_INVALID, "n_traced out of range");
+    if (batch < 0) return fail(BQ_ERR_INVALID, "negative batch");
+    if (batch > 1 && psi_stride < ((int64_t)1 << n_qubits)) return fail(BQ_ERR_INVALID, "psi_stride smaller than 2^n_qubits");
+    if (batch > 0 && (!psi || !out)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    return BQ_OK;
+}
+
+struct HostTimer {
+    bq_handle_t h;
+    explicit HostTimer(bq_handle_t hh) : h(hh) { cudaEventRecord(h->ev_t0, h->stream); }
+    int finish()
+    {
+        CU(cudaEventRecord(h->ev_t1, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+        h->last_ms = ms;
+        return BQ_OK;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int bq_version(void) { return BQ_B200_VERSION; }
+const char *bq_last_error(void) { return g_err.c_str(); }
+
+int bq_device_count(int *count)
+{
+    if (!count) return fail(BQ_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail_cuda(e, "cudaGetDeviceCount");
+    }
+    *count = n;
+    return BQ_OK;
+}
+
+int bq_create(bq_handle_t *out, int device)
+{
+    if (!out) return fail(BQ_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(BQ_ERR_NO_DEVICE, std::string("no CUDA device available (there is no CPU fallback): ") +
+                                          (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= n) return fail(BQ_ERR_NO_DEVICE, "device ordinal out of range");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BQ_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(BQ_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200) class");
+    bq_handle_s *h = new bq_handle_s();
+    h->dev.device = device;
+    h->dev.sm_count = prop.multiProcessorCount;
+    h->dev.smem_optin = prop.sharedMemPerBlockOptin;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreate(&h->ev_t0) == cudaSuccess && cudaEventCreate(&h->ev_t1) == cudaSuccess &&
+              cudaMalloc(&h->ctr, sizeof(unsigned int) * 2 * kCtrSlots) == cudaSuccess &&
+              cudaMemset(h->ctr, 0, sizeof(unsigned int) * 2 * kCtrSlots) == cudaSuccess;
+    if (!ok) {
+        cudaError_t le = cudaGetLastError();
+        bq_destroy(h);
+        return fail_cuda(le, "bq_create resources");
+    }
+    *out = h;
+    return BQ_OK;
+}
+
+int bq_destroy(bq_handle_t h)
+{
+    if (!h) return BQ_OK;
+    {
+        DeviceGuard guard(h->dev.device);
+        cudaDeviceSynchronize();
+        for (auto &kv : h->tabs) cudaFree(kv.second);
+        for (auto &kv : h->maps) cudaFree(kv.second);
+        Buffer *bufs[] = {&h->cs, &h->partial, &h->rho_tmp, &h->in_dev, &h->out_dev, &h->rho_dev, &h->grid_dev, &h->small_dev};
+        for (Buffer *b : bufs) b->release();
+        for (auto &pr : h->prof_events) {
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        if (h->ctr) cudaFree(h->ctr);
+        if (h->ev_order) cudaEventDestroy(h->ev_order);
+        if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+        if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+    return BQ_OK;
+}
+
+int bq_device(bq_handle_t h, int *device)
+{
+    if (!h || !device) return fail(BQ_ERR_INVALID, "NULL argument");
+    *device = h->dev.device;
+    return BQ_OK;
+}
+
+int bq_launch_count(bq_handle_t h, uint64_t *count)
+{
+    if (!h || !count) return fail(BQ_ERR_INVALID, "NULL argument");
+    *count = h->launches;
+    return BQ_OK;
+}
+
+int bq_synchronize(bq_handle_t h)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    DeviceGuard guard(h->dev.device);
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->have_last) CU(cudaStreamSynchronize(h->last_stream));
+    return BQ_OK;
+}
+
+int bq_host_alloc(bq_handle_t h, size_t bytes, void **out)
+{
+    if (!h || !out) return fail(BQ_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->dev.device);
+    CU(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+    return BQ_OK;
+}
+
+int bq_host_free(bq_handle_t h, void *ptr)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (!ptr) return BQ_OK;
+    DeviceGuard guard(h->dev.device);
+    CU(cudaFreeHost(ptr));
+    return BQ_OK;
+}
+
+// ---- partial trace -----------------------------------------------------------------------------
+int bq_partial_trace_sv_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                            int batch, int64_t psi_stride, double *d_rho_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_trace_args(d_psi, n_qubits, n_traced, batch, psi_stride, d_rho_out);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    return trace_sv_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, 1, batch, psi_stride,
+                         (double2 *)d_rho_out, st);
+}
+
+int bq_partial_trace_sv_multi_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced,
+                                  int n_traced, int n_sets, double *d_rho_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_trace_args(d_psi, n_qubits, n_traced, 1, 0, d_rho_out);
+    if (rc) return rc;
+    if (n_sets < 0 || n_sets > 4096) return fail(BQ_ERR_INVALID, "n_sets out of range [0, 4096]");
+    if (n_sets == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    return trace_sv_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, n_sets, 1, 0, (double2 *)d_rho_out, st);
+}
+
+static int trace_sv_host_common(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                int n_sets, int batch, int64_t psi_stride, double *rho_out)
+{
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    int rc = order_stream(h, h->stream);
+    if (rc) return rc;
+    const int64_t dim = (int64_t)1 << n_qubits;
+    const int64_t D = (int64_t)1 << (n_qubits - n_traced);
+    const size_t in_elems = batch ? (size_t)((int64_t)(batch - 1) * psi_stride + dim) : 0;
+    const size_t out_elems = (size_t)n_sets * batch * D * D;
+    if (!in_elems || !out_elems) return BQ_OK;
+    CU(h->in_dev.reserve(in_elems * sizeof(double2)));
+    CU(h->rho_dev.reserve(out_elems * sizeof(double2)));
+    HostTimer timer(h);
+    CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    rc = trace_sv_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, n_sets, batch, psi_stride,
+                       (double2 *)h->rho_dev.ptr, h->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, out_elems * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
+}
+
+int bq_partial_trace_sv_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                             int batch, int64_t psi_stride, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_trace_args(psi, n_qubits, n_traced, batch, psi_stride, rho_out);
+    if (rc) return rc;
+    return trace_sv_host_common(h, psi, n_qubits, traced, n_traced, 1, batch, psi_stride, rho_out);
+}
+
+int bq_partial_trace_sv_multi_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced,
+                                   int n_traced, int n_sets, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_trace_args(psi, n_qubits, n_traced, 1, 0, rho_out);
+    if (rc) return rc;
+    if (n_sets < 0 || n_sets > 4096) return fail(BQ_ERR_INVALID, "n_sets out of range [0, 4096]");
+    if (n_sets == 0) return BQ_OK;
+    return trace_sv_host_common(h, psi, n_qubits, traced, n_traced, n_sets, 1, 0, rho_out);
+}
+
+static int trace_dm_core(bq_handle_t h, const double2 *d_rho, int n_qubits, const int *traced, int n_traced, int batch,
+                         double2 *d_out, cudaStream_t st)
+{
+    const bq::TraceMap *maps = nullptr;
+    int rc = get_maps(h, n_qubits, traced, n_traced, 1, &maps);
+    if (rc) return rc;
+    int nl = 0;
+    cudaError_t e = bq::launch_trace_dm(d_rho, n_qubits, batch, maps, n_qubits - n_traced, n_traced, d_out, st, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(e, "launch_trace_dm");
+    return BQ_OK;
+}
+
+static int check_dm_args(const void *rho, int n_qubits, int n_traced, int batch, const void *out)
+{
+    if (n_qubits < 0 || n_qubits > 15) return fail(BQ_ERR_INVALID, "density matrix n_qubits out of range [0, 15]");
+    if (n_traced < 0 || n_traced > n_qubits) return fail(BQ_ERR_INVALID, "n_traced out of range");
+    if (batch < 0) return fail(BQ_ERR_INVALID, "negative batch");
+    if (batch > 0 && (!rho || !out)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    return BQ_OK;
+}
+
+int bq_partial_trace_dm_dev(bq_handle_t h, const double *d_rho, int n_qubits, const int *traced, int n_traced,
+                            int batch, double *d_rho_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_dm_args(d_rho, n_qubits, n_traced, batch, d_rho_out);
+    if (rc) return rc;
+    if (batch == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    return trace_dm_core(h, (const double2 *)d_rho, n_qubits, traced, n_traced, batch, (double2 *)d_rho_out, st);
+}
+
+int bq_partial_trace_dm_host(bq_handle_t h, const double *rho, int n_qubits, const int *traced, int n_traced,
+                             int batch, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_dm_args(rho, n_qubits, n_traced, batch, rho_out);
+    if (rc) return rc;
+    if (batch == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    if ((rc = order_stream(h, h->stream))) return rc;
+    const int64_t F = (int64_t)1 << n_qubits, D = (int64_t)1 << (n_qubits - n_traced);
+    const size_t in_b = (size_t)batch * F * F * sizeof(double2), out_b = (size_t)batch * D * D * sizeof(double2);
+    CU(h->in_dev.reserve(in_b));
+    CU(h->rho_dev.reserve(out_b));
+    HostTimer timer(h);
+    CU(cudaMemcpyAsync(h->in_dev.ptr, rho, in_b, cudaMemcpyHostToDevice, h->stream));
+    rc = trace_dm_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, batch, (double2 *)h->rho_dev.ptr,
+                       h->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
+}
+
+int bq_photon_number_dev(bq_handle_t h, const double *d_rho, int D, int batch, double *d_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (D < 1 || batch < 0) return fail(BQ_ERR_INVALID, "bad size");
+    if (batch == 0) return BQ_OK;
+    if (!d_rho || !d_out) return fail(BQ_ERR_INVALID, "NULL pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = order_stream(h, st);
+    if (rc) return rc;
+    int nl = 0;
+    cudaError_t e = bq::launch_photon_number((const double2 *)d_rho, D, batch, (double2 *)d_out, st, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(e, "launch_photon_number");
+    return BQ_OK;
+}
+
+int bq_photon_number_host(bq_handle_t h, const double *rho, int D, int batch, double *out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (D < 1 || batch < 0) return fail(BQ_ERR_INVALID, "bad size");
+    if (batch == 0) return BQ_OK;
+    if (!rho || !out) return fail(BQ_ERR_INVALID, "NULL pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    int rc = order_stream(h, h->stream);
+    if (rc) return rc;
+    const size_t in_b = (size_t)batch * D * D * sizeof(double2), out_b = (size_t)batch * sizeof(double2);
+    CU(h->in_dev.reserve(in_b));
+    CU(h->small_dev.reserve(out_b));
+    HostTimer timer(h);
+    CU(cudaMemcpyAsync(h->in_dev.ptr, rho, in_b, cudaMemcpyHostToDevice, h->stream));
+    int nl = 0;
+    cudaError_t e = bq::launch_photon_number((const double2 *)h->in_dev.ptr, D, batch, (double2 *)h->small_dev.ptr,
+                                             h->stream, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(e, "launch_photon_number");
+    CU(cudaMemcpyAsync(out, h->small_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
+}
+
+// ---- Wigner ------------------------------------------------------------------------------------
+int bq_wigner_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                  const double *d_xvec, int nx, const double *d_yvec, int ny, double g, int method,
+                  double *d_W_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_method(method);
+    if (rc) return rc;
+    if ((rc = check_wigner_args(d_rho, N, ld, rho_stride, batch, d_xvec, nx, d_yvec, ny, g, d_W_out))) return rc;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    return wigner_core(h, (const double2 *)d_rho, N, ld, rho_stride, batch, d_xvec, nx, d_yvec, ny, g, d_W_out, st);
+}
+
+int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                   const double *xvec, int nx, const double *yvec, int ny, double g, int method, double *W_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_method(method);
+    if (rc) return rc;
+    if ((rc = check_wigner_args(rho, N, ld, rho_stride, batch, xvec, nx, yvec, ny, g, W_out))) return rc;
+    if (batch == 0 || nx == 0 || ny == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    if ((rc = order_stream(h, h->stream))) return rc;
+    const double *dx, *dy;
+    if ((rc = stage_grid(h, xvec, nx, yvec, ny, &dx, &dy))) return rc;
+    const size_t in_elems = (size_t)((int64_t)(batch - 1) * rho_stride + (int64_t)(N - 1) * ld + N);
+    const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
+    CU(h->in_dev.reserve(in_elems * sizeof(double2)));
+    CU(h->out_dev.reserve(out_b));
+    HostTimer timer(h);
+    CU(cudaMemcpyAsync(h->in_dev.ptr, rho, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    rc = wigner_core(h, (const double2 *)h->in_dev.ptr, N, ld, rho_stride, batch, dx, nx, dy, ny, g,
+                     (double *)h->out_dev.ptr, h->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
+}
+
+// ---- fused frame loop --------------------------------------------------------------------------
+static int state_to_wigner_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced,
+                                int batch, int64_t psi_stride, const double *dx, int nx, const double *dy, int ny,
+                                double g, double *d_W, double2 *d_rho_opt, cudaStream_t st)
+{
+    const int n_keep = n_qubits - n_traced;
+    if (n_keep > 14) return fail(BQ_ERR_INVALID, "reduced density matrix larger than 2^14 x 2^14");
+    const int64_t D = (int64_t)1 << n_keep;
+    double2 *d_rho = d_rho_opt;
+    if (!d_rho) {
+        CU(h->rho_tmp.reserve((size_t)batch * D * D * sizeof(double2)));
+        d_rho = (double2 *)h->rho_tmp.ptr;
+    }
+    int rc = trace_sv_core(h, d_psi, n_qubits, traced, n_traced, 1, batch, psi_stride, d_rho, st);
+    if (rc) return rc;
+    return wigner_core(h, d_rho, (int)D, D, D * D, batch, dx, nx, dy, ny, g, d_W, st);
+}
+
+int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                           int batch, int64_t psi_stride, const double *d_xvec, int nx, const double *d_yvec,
+                           int ny, double g, int method, double *d_W_out, double *d_rho_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_method(method);
+    if (rc) return rc;
+    if ((rc = check_trace_args(d_psi, n_qubits, n_traced, batch, psi_stride, d_W_out))) return rc;
+    if (nx < 0 || ny < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (batch > 0 && nx > 0 && ny > 0 && (!d_xvec || !d_yvec)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    if (!std::isfinite(g)) return fail(BQ_ERR_INVALID, "g is not finite");
+    if (batch == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    return state_to_wigner_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, batch, psi_stride, d_xvec, nx,
+                                d_yvec, ny, g, d_W_out, (double2 *)d_rho_out, st);
+}
+
+int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                            int batch, int64_t psi_stride, const double *xvec, int nx, const double *yvec,
+                            int ny, double g, int method, double *W_out, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_method(method);
+    if (rc) return rc;
+    if ((rc = check_trace_args(psi, n_qubits, n_traced, batch, psi_stride, W_out))) return rc;
+    if (nx < 0 || ny < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (batch > 0 && nx > 0 && ny > 0 && (!xvec || !yvec)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    if (!std::isfinite(g)) return fail(BQ_ERR_INVALID, "g is not finite");
+    if (batch == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    if ((rc = order_stream(h, h->stream))) return rc;
+    const double *dx, *dy;
+    if ((rc = stage_grid(h, xvec, nx, yvec, ny, &dx, &dy))) return rc;
+    const int64_t dim = (int64_t)1 << n_qubits, D = (int64_t)1 << (n_qubits - n_traced);
+    const size_t in_elems = (size_t)((int64_t)(batch - 1) * psi_stride + dim);
+    const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
+    const size_t rho_b = (size_t)batch * D * D * sizeof(double2);
+    CU(h->in_dev.reserve(in_elems * sizeof(double2)));
+    CU(h->out_dev.reserve(std::max<size_t>(out_b, 8)));
+    CU(h->rho_dev.reserve(rho_b));
+    HostTimer timer(h);
+    CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, batch, psi_stride, dx, nx,
+                              dy, ny, g, (double *)h->out_dev.ptr, (double2 *)h->rho_dev.ptr, h->stream);
+    if (rc) return rc;
+    if (rho_out) CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, rho_b, cudaMemcpyDeviceToHost, h->stream));
+    if (out_b) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
+}
+
+int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, double *d_out,
+                        void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (points_per_frame < 0 || batch < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (batch == 0) return BQ_OK;
+    if (!d_W || !d_out) return fail(BQ_ERR_INVALID, "NULL pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = order_stream(h, st);
+    if (rc) return rc;
+    int nl = 0;
+    cudaError_t e = bq::launch_frame_minmax(d_W, points_per_frame, batch, (double2 *)d_out, st, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(e, "launch_frame_minmax");
+    return BQ_OK;
+}
+
+// ---- measurement helpers -----------------------------------------------------------------------
+int bq_fp64_peak(bq_handle_t h, double seconds, double *tflops)
+{
+    if (!h || !tflops) return fail(BQ_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    CU(h->small_dev.reserve(64));
+    const int grid = h->dev.sm_count * 8;
+    const int iters = 4096;
+    const double flops_per_launch = (double)grid * 256.0 * iters * 16.0 * 8.0 * 2.0;
+    // warm-up
+    for (int i = 0; i < 3; ++i) CU(bq::launch_fp64_probe((double *)h->small_dev.ptr, iters, grid, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    double best = 0.0, total_ms = 0.0;
+    int rounds = 0;
+    while (total_ms < seconds * 1e3 && rounds < 100000) {
+        CU(cudaEventRecord(h->ev_t0, h->stream));
+        for (int i = 0; i < 4; ++i) CU(bq::launch_fp64_probe((double *)h->small_dev.ptr, iters, grid, h->stream));
+        CU(cudaEventRecord(h->ev_t1, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+        total_ms += ms;
+        ++rounds;
+        // sustained figure: the LAST rounds (clocks settled under load), not the best burst
+        best = 4.0 * flops_per_launch / (ms * 1e-3) / 1e12;
+    }
+    *tflops = best;
+    return BQ_OK;
+}
+
+int bq_last_device_ms(bq_handle_t h, double *ms)
+{
+    if (!h || !ms) return fail(BQ_ERR_INVALID, "NULL argument");
+    *ms = h->last_ms;
+    return BQ_OK;
+}
+
+int bq_profile_enable(bq_handle_t h, int on)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->profile = on != 0;
+    return BQ_OK;
+}
+
+int bq_profile_read(bq_handle_t h, double *total_ms, int *launches)
+{
+    if (!h || !total_ms || !launches) return fail(BQ_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    double tot = 0.0;
+    int n = 0;
+    for (auto &pr : h->prof_events) {
+        CU(cudaEventSynchronize(pr.second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        ++n;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    h->prof_events.clear();
+    *total_ms = tot;
+    *launches = n;
+    return BQ_OK;
+}
+
+// ---- CUDA IPC ----------------------------------------------------------------------------------
+int bq_ipc_export(bq_handle_t h, void *d_ptr, unsigned char *handle64)
+{
+    if (!h || !d_ptr || !handle64) return fail(BQ_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    DeviceGuard guard(h->dev.device);
+    cudaIpcMemHandle_t mh;
+    CU(cudaIpcGetMemHandle(&mh, d_ptr));
+    std::memcpy(handle64, &mh, 64);
+    return BQ_OK;
+}
+
+int bq_ipc_open(bq_handle_t h, const unsigned char *handle64, void **d_ptr)
+{
+    if (!h || !handle64 || !d_ptr) return fail(BQ_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->dev.device);
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, handle64, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    return BQ_OK;
+}
+
+int bq_ipc_close(bq_handle_t h, void *d_ptr)
+{
+    if (!h || !d_ptr) return fail(BQ_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->dev.device);
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return BQ_OK;
+}
+
+}  // extern "C"

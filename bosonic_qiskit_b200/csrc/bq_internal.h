@@ -1,0 +1,69 @@
+// Internal host-side declarations shared by the kernel translation units and the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bq {
+
+constexpr int kResidentMaxN = 64;  // stream fits twice per SM in shared memory up to this cutoff
+constexpr int kMaxQubits = 40;
+constexpr int kKernelSlots = 16;
+
+// records in the coefficient stream of cutoff N, and the first record of the diagonal with K = N-L
+// coefficients (K >= 2); layout described in bq_common.cuh
+__host__ __device__ inline int64_t stream_records(int N) { return (int64_t)N * (N + 1) / 2 + N - 1; }
+__host__ __device__ inline int64_t diag_pos(int K) { return ((int64_t)K * K + K - 4) / 2; }
+
+struct DeviceInfo {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // per-kernel launch cache (attribute set once, occupancy looked up once per shared-memory size)
+    bool configured[kKernelSlots] = {};
+    int occ[kKernelSlots] = {};
+    size_t occ_smem[kKernelSlots] = {};
+};
+
+struct WigParams {
+    const double2 *cs;   // [batch][R_tot] rho-dependent stream
+    const double4 *tab;  // [R_tot] recurrence constants
+    const double *xvec, *yvec;
+    double *W;  // [batch][ny][nx]
+    int64_t w_stride, cs_stride;
+    int N, R_tot, nx, ny, batch;
+    int chunks_per_row, tiles_per_frame, total_tiles, grab, vec_ok;
+    double g, scale;
+    unsigned int *ctr;  // [0] next tile, [1] CTAs that left
+};
+
+struct TraceMap {
+    // bit positions (ascending significance) of kept and traced qubits in the statevector index
+    int keep[kMaxQubits];
+    int trace[kMaxQubits];
+    int n_keep, n_trace;
+};
+
+cudaError_t launch_build_tab(double4 *tab, int N, cudaStream_t st);
+cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, int N, int batch, double2 *cs,
+                            int64_t cs_stride, cudaStream_t st);
+cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches);
+
+// K1: rho[set][b] = Psi Psi^dagger.  `maps` is a device array of n_sets TraceMaps (same n_keep / n_trace);
+// rho_out is [n_sets][batch][D][D]; `partial` is scratch of at least trace_sv_scratch_bytes().
+size_t trace_sv_scratch_bytes(int n_keep, int n_trace, int batch, int n_sets);
+cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, const TraceMap *d_maps, int n_sets,
+                            int n_keep, int n_trace, double2 *rho_out, double2 *partial, const DeviceInfo &dev,
+                            cudaStream_t st, int *launches);
+// K2: density-matrix branch
+cudaError_t launch_trace_dm(const double2 *rho, int n_qubits, int batch, const TraceMap *d_map, int n_keep,
+                            int n_trace, double2 *rho_out, cudaStream_t st, int *launches);
+// K5: <n> per batch element, out[b] = (re, im)
+cudaError_t launch_photon_number(const double2 *rho, int D, int batch, double2 *out, cudaStream_t st, int *launches);
+// per-frame (min, max)
+cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, double2 *out, cudaStream_t st,
+                                int *launches);
+// FP64 DFMA peak probe: runs `iters` rounds of 8 independent chains x 16 FMAs per thread
+cudaError_t launch_fp64_probe(double *sink, int iters, int grid, cudaStream_t st);
+
+}  // namespace bq

@@ -1,0 +1,370 @@
+// K1 / K2 / K5: partial traces and small reductions, fp64 complex, sm_100a.
+//
+// Replaces qiskit.quantum_info.partial_trace(state, qargs) as called from
+// src/bosonic_qiskit/util.py:580 (trace_out_qumodes), :596 (trace_out_qubits), :619
+// (cv_partial_trace) and :693 (the per-qumode loop of avg_photon_num), plus the <n> expectation
+// of util.qumode_avg_photon_num (util.py:699-736).
+//
+// Statevector branch: rho_keep = Psi Psi^dagger with Psi[i, t] = psi[dep_keep(i) | dep_trace(t)] -- the
+// kept qubits, in their original significance order, form the row index; the gather by
+// bit-deposit is fused into the operand load (no transposed copy of psi is ever made, unlike the
+// two transposes inside numpy.tensordot).
+#include <algorithm>
+
+#include "bq_common.cuh"
+#include "bq_internal.h"
+
+namespace bq {
+
+__device__ __forceinline__ uint64_t deposit_bits(uint64_t v, const int *pos, int n)
+{
+    uint64_t r = 0;
+    for (int b = 0; b < n; ++b) r |= ((v >> b) & 1ull) << pos[b];
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1.  One CTA = one TI x TJ tile of one rho, one split of the traced range.
+// 256 threads = TI*TJ outputs x LT lanes along t.  Operands are staged in shared memory in chunks of
+// TC traced indices; accumulation order over t is fixed (deterministic results).
+// ------------------------------------------------------------------------------------------------
+constexpr int kTraceThreads = 256;
+constexpr int kTC = 32;
+
+struct TraceSvParams {
+    const double2 *psi;
+    int64_t psi_stride;
+    const TraceMap *maps;
+    double2 *out;  // final rho or partials: [split][set][batch][D][D]
+    int n_keep, n_trace, batch, n_sets, splits;
+    int TI, TJ, LT;
+    int tiles_i, tiles_j;
+    int64_t t_per_split;
+};
+
+__global__ void __launch_bounds__(kTraceThreads) trace_sv_kernel(const TraceSvParams p)
+{
+    __shared__ double2 As[16][kTC + 1];
+    __shared__ double2 Bs[16][kTC + 1];
+    __shared__ uint64_t row_i[16], row_j[16], toff[kTC];
+    __shared__ double2 red[kTraceThreads];
+    __shared__ TraceMap map;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int split = blockIdx.y;
+    const int sb = blockIdx.z;  // set * batch + b
+    const int set = sb / p.batch, b = sb - set * p.batch;
+    const int ti0 = (tile / p.tiles_j) * p.TI, tj0 = (tile % p.tiles_j) * p.TJ;
+
+    // the map is small: copy it once per CTA
+    {
+        const int *src = reinterpret_cast<const int *>(p.maps + set);
+        int *dst = reinterpret_cast<int *>(&map);
+        for (int i = tid; i < (int)(sizeof(TraceMap) / sizeof(int)); i += kTraceThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    if (tid < p.TI) row_i[tid] = deposit_bits((uint64_t)(ti0 + tid), map.keep, p.n_keep);
+    if (tid >= 32 && tid < 32 + p.TJ) row_j[tid - 32] = deposit_bits((uint64_t)(tj0 + tid - 32), map.keep, p.n_keep);
+
+    const double2 *psi = p.psi + (int64_t)b * p.psi_stride;
+    const int64_t T = (int64_t)1 << p.n_trace;
+    const int64_t t_begin = (int64_t)split * p.t_per_split;
+    const int64_t t_end = min(T, t_begin + p.t_per_split);
+
+    const int outs = p.TI * p.TJ;
+    const int o = tid % outs, lane_t = tid / outs;  // LT = 256 / outs lanes share one output
+    const int oi = o / p.TJ, oj = o % p.TJ;
+    double accr = 0.0, acci = 0.0;
+
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += kTC) {
+        const int nt = (int)min((int64_t)kTC, t_end - t0);
+        __syncthreads();  // previous chunk consumed (also orders row_i/row_j on the first pass)
+        if (tid < nt) toff[tid] = deposit_bits((uint64_t)(t0 + tid), map.trace, p.n_trace);
+        __syncthreads();
+        for (int e = tid; e < p.TI * kTC; e += kTraceThreads) {
+            const int r = e / kTC, c = e % kTC;
+            As[r][c] = (c < nt) ? psi[row_i[r] | toff[c]] : make_double2(0.0, 0.0);
+        }
+        for (int e = tid; e < p.TJ * kTC; e += kTraceThreads) {
+            const int r = e / kTC, c = e % kTC;
+            Bs[r][c] = (c < nt) ? psi[row_j[r] | toff[c]] : make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        for (int c = lane_t; c < kTC; c += p.LT) {
+            const double2 x = As[oi][c], y = Bs[oj][c];
+            // x * conj(y)
+            accr = fma(x.x, y.x, fma(x.y, y.y, accr));
+            acci = fma(x.y, y.x, fma(-x.x, y.y, acci));
+        }
+    }
+    red[tid] = make_double2(accr, acci);
+    __syncthreads();
+    if (lane_t == 0) {
+        for (int l = 1; l < p.LT; ++l) {
+            const double2 v = red[l * outs + o];
+            accr += v.x;
+            acci += v.y;
+        }
+        const int64_t D = (int64_t)1 << p.n_keep;
+        double2 *dst = p.out + (((int64_t)split * p.n_sets + set) * p.batch + b) * D * D;
+        dst[(int64_t)(ti0 + oi) * D + (tj0 + oj)] = make_double2(accr, acci);
+    }
+}
+
+__global__ void reduce_splits_kernel(const double2 *__restrict__ partial, double2 *__restrict__ out, int64_t count,
+                                     int splits)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double re = 0.0, im = 0.0;
+    for (int s = 0; s < splits; ++s) {
+        const double2 v = partial[(int64_t)s * count + i];
+        re += v.x;
+        im += v.y;
+    }
+    out[i] = make_double2(re, im);
+}
+
+namespace {
+struct TracePlan {
+    int TI, TJ, LT, tiles_i, tiles_j, splits;
+    int64_t t_per_split;
+};
+
+TracePlan plan_trace(int n_keep, int n_trace, int batch, int n_sets, int sm_count)
+{
+    TracePlan pl;
+    const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_trace;
+    pl.TI = (int)std::min<int64_t>(D, 16);
+    pl.TJ = pl.TI;
+    pl.LT = kTraceThreads / (pl.TI * pl.TJ);
+    pl.tiles_i = (int)(D / pl.TI);
+    pl.tiles_j = pl.tiles_i;
+    const int64_t ctas = (int64_t)pl.tiles_i * pl.tiles_j * batch * n_sets;
+    const int64_t want = 2LL * sm_count;
+    int64_t splits = 1;
+    if (ctas < want) splits = (want + ctas - 1) / ctas;
+    const int64_t max_splits = std::max<int64_t>(1, T / 128);  // at least 128 traced indices per split
+    splits = std::min(splits, max_splits);
+    splits = std::min<int64_t>(splits, 1024);
+    int64_t per = (T + splits - 1) / splits;
+    per = (per + kTC - 1) / kTC * kTC;
+    splits = (T + per - 1) / per;
+    pl.splits = (int)splits;
+    pl.t_per_split = per;
+    return pl;
+}
+}  // namespace
+
+size_t trace_sv_scratch_bytes(int n_keep, int n_trace, int batch, int n_sets)
+{
+    // worst case over devices: plan with a generous SM count so the scratch never under-sizes
+    const TracePlan pl = plan_trace(n_keep, n_trace, batch, n_sets, 256);
+    const int64_t D = (int64_t)1 << n_keep;
+    return (size_t)pl.splits * n_sets * batch * D * D * sizeof(double2);
+}
+
+cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, const TraceMap *d_maps, int n_sets,
+                            int n_keep, int n_trace, double2 *rho_out, double2 *partial, const DeviceInfo &dev,
+                            cudaStream_t st, int *launches)
+{
+    if (batch <= 0 || n_sets <= 0) return cudaSuccess;
+    const TracePlan pl = plan_trace(n_keep, n_trace, batch, n_sets, dev.sm_count);
+    TraceSvParams p;
+    p.psi = psi;
+    p.psi_stride = psi_stride;
+    p.maps = d_maps;
+    p.n_keep = n_keep;
+    p.n_trace = n_trace;
+    p.batch = batch;
+    p.n_sets = n_sets;
+    p.splits = pl.splits;
+    p.TI = pl.TI;
+    p.TJ = pl.TJ;
+    p.LT = pl.LT;
+    p.tiles_i = pl.tiles_i;
+    p.tiles_j = pl.tiles_j;
+    p.t_per_split = pl.t_per_split;
+    p.out = (pl.splits > 1) ? partial : rho_out;
+    const int64_t zdim = (int64_t)batch * n_sets;
+    if (zdim > 65535 || (int64_t)pl.tiles_i * pl.tiles_j > 0x7fffffffLL) return cudaErrorInvalidValue;
+    dim3 grid(pl.tiles_i * pl.tiles_j, pl.splits, (unsigned)zdim);
+    trace_sv_kernel<<<grid, kTraceThreads, 0, st>>>(p);
+    if (launches) ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (pl.splits > 1) {
+        const int64_t D = (int64_t)1 << n_keep;
+        const int64_t count = (int64_t)n_sets * batch * D * D;
+        reduce_splits_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partial, rho_out, count, pl.splits);
+        if (launches) ++*launches;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2.  rho_keep[i, j] = sum_t rho[(i,t), (j,t)]; one warp per output element, lanes stride over t,
+// warp-shuffle reduction.
+// ------------------------------------------------------------------------------------------------
+__global__ void trace_dm_kernel(const double2 *__restrict__ rho, int n_qubits, int batch, const TraceMap *maps,
+                                int n_keep, int n_trace, double2 *__restrict__ out)
+{
+    __shared__ TraceMap map;
+    {
+        const int *src = reinterpret_cast<const int *>(maps);
+        int *dst = reinterpret_cast<int *>(&map);
+        for (int i = threadIdx.x; i < (int)(sizeof(TraceMap) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_trace, F = (int64_t)1 << n_qubits;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= D * D * batch) return;
+    const int64_t b = warp / (D * D), ij = warp - b * D * D;
+    const int64_t i = ij / D, j = ij - i * D;
+    const uint64_t bi = deposit_bits((uint64_t)i, map.keep, n_keep), bj = deposit_bits((uint64_t)j, map.keep, n_keep);
+    const double2 *R = rho + b * F * F;
+    double re = 0.0, im = 0.0;
+    for (int64_t t = lane; t < T; t += 32) {
+        const uint64_t o = deposit_bits((uint64_t)t, map.trace, n_trace);
+        const double2 v = R[(int64_t)(bi | o) * F + (int64_t)(bj | o)];
+        re += v.x;
+        im += v.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        re += __shfl_down_sync(0xffffffffu, re, off);
+        im += __shfl_down_sync(0xffffffffu, im, off);
+    }
+    if (lane == 0) out[warp] = make_double2(re, im);
+}
+
+cudaError_t launch_trace_dm(const double2 *rho, int n_qubits, int batch, const TraceMap *d_map, int n_keep,
+                            int n_trace, double2 *rho_out, cudaStream_t st, int *launches)
+{
+    const int64_t D = (int64_t)1 << n_keep;
+    const int64_t warps = D * D * batch;
+    if (warps <= 0) return cudaSuccess;
+    const int64_t blocks = (warps * 32 + 255) / 256;
+    if (blocks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    trace_dm_kernel<<<(unsigned)blocks, 256, 0, st>>>(rho, n_qubits, batch, d_map, n_keep, n_trace, rho_out);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5.  <n> = sum_n n rho_nn / sum_n rho_nn; one warp per batch element.
+// ------------------------------------------------------------------------------------------------
+__global__ void photon_number_kernel(const double2 *__restrict__ rho, int D, int batch, double2 *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= batch) return;
+    const double2 *R = rho + (int64_t)b * D * D;
+    double nr = 0.0, ni = 0.0, tr = 0.0, ti = 0.0;
+    for (int n = lane; n < D; n += 32) {
+        const double2 v = R[(int64_t)n * D + n];
+        nr = fma((double)n, v.x, nr);
+        ni = fma((double)n, v.y, ni);
+        tr += v.x;
+        ti += v.y;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        nr += __shfl_down_sync(0xffffffffu, nr, off);
+        ni += __shfl_down_sync(0xffffffffu, ni, off);
+        tr += __shfl_down_sync(0xffffffffu, tr, off);
+        ti += __shfl_down_sync(0xffffffffu, ti, off);
+    }
+    if (lane == 0) {
+        const double den = tr * tr + ti * ti;
+        out[b] = make_double2((nr * tr + ni * ti) / den, (ni * tr - nr * ti) / den);
+    }
+}
+
+cudaError_t launch_photon_number(const double2 *rho, int D, int batch, double2 *out, cudaStream_t st, int *launches)
+{
+    if (batch <= 0) return cudaSuccess;
+    photon_number_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(rho, D, batch, out);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-frame (min, max): one CTA per frame, warp-shuffle + shared-memory reduction
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) frame_minmax_kernel(const double *__restrict__ W, int64_t points,
+                                                            double2 *__restrict__ out)
+{
+    __shared__ double smin[32], smax[32];
+    const double *F = W + (int64_t)blockIdx.x * points;
+    double lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = threadIdx.x; i < points; i += blockDim.x) {
+        const double v = F[i];
+        lo = fmin(lo, v);
+        hi = fmax(hi, v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, off));
+        hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, off));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) {
+        smin[w] = lo;
+        smax[w] = hi;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+        lo = lane < nw ? smin[lane] : INFINITY;
+        hi = lane < nw ? smax[lane] : -INFINITY;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            lo = fmin(lo, __shfl_down_sync(0xffffffffu, lo, off));
+            hi = fmax(hi, __shfl_down_sync(0xffffffffu, hi, off));
+        }
+        if (lane == 0) out[blockIdx.x] = make_double2(lo, hi);
+    }
+}
+
+cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, double2 *out, cudaStream_t st,
+                                int *launches)
+{
+    if (batch <= 0) return cudaSuccess;
+    frame_minmax_kernel<<<batch, 1024, 0, st>>>(W, points, out);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak probe: 8 independent DFMA chains per thread, nothing else in the loop body.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *sink, int iters)
+{
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+    const double m = 1.0 - 1e-12, c = 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+    if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
+}
+
+cudaError_t launch_fp64_probe(double *sink, int iters, int grid, cudaStream_t st)
+{
+    fp64_probe_kernel<<<grid, 256, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace bq

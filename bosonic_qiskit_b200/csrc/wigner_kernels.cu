@@ -1,0 +1,453 @@
+// K3: Wigner quasi-probability grid by outer Horner / inner Clenshaw, fp64, sm_100a.
+//
+// Replaces qutip.wigner(Qobj(rho), xvec, yvec, g, method="clenshaw") as called from
+// src/bosonic_qiskit/wigner.py:190 (and, batched, the frame loops at wigner.py:92-96 and
+// animate.py:326-352).  The recurrences are those of qutip 5.2.2 `_wigner_clenshaw` /
+// `_wig_laguerre_val`; see bq_common.cuh for how rho and the recurrence constants are laid out as
+// one linear coefficient stream.
+//
+// Design (FP64-pipe bound: ~5 N^2 flops per 8-byte output):
+//   * each thread owns PTS contiguous x-points of one grid row; all state (y0, y1, w0 complex, B, A2)
+//     stays in registers; the inner step is 5 DFMA per point and nothing else on the fp64 pipe;
+//   * every coefficient is a shared-memory broadcast (LDS.128) shared by the whole CTA;
+//   * N <= 64: the whole stream is resident in shared memory (bulk-copied once per CTA, the rho part
+//     again whenever the CTA moves to another frame);
+//   * N  > 64: the stream is pulled through a STAGES-deep shared-memory ring with cp.async.bulk
+//     (1-D TMA) + mbarrier full/empty pairs, one elected producer thread, every warp a consumer;
+//   * persistent CTAs take tiles from a global counter so that all 148 SMs finish together;
+//   * stores are 32 B per thread, 1 KiB contiguous per warp, streaming (evict-first).
+#include "bq_common.cuh"
+#include "bq_internal.h"
+
+namespace bq {
+
+// ------------------------------------------------------------------------------------------------
+// constant table and rho packing (tiny setup kernels)
+// ------------------------------------------------------------------------------------------------
+__global__ void build_tab_kernel(double4 *__restrict__ tab, int N)
+{
+    const int K = blockIdx.x + 2;  // diagonal with K coefficients, L = N-K
+    if (blockIdx.x == 0 && threadIdx.x == 0) tab[0] = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (K > N) return;
+    const int L = N - K;
+    const int64_t pos = diag_pos(K);
+    for (int r = threadIdx.x; r <= K; r += blockDim.x) {
+        double4 t;
+        if (r < K) {
+            const int k = (K - 1 - r) + 2;
+            const double den = (double)(L + k) * (double)k;
+            const double s = 1.0 / sqrt(den);
+            t.x = -sqrt(((double)(k - 1) * (double)(L + k - 1)) / den);
+            t.y = -(double)(L + 2 * k - 1) * s;
+            t.z = s;
+            t.w = 0.0;
+        } else {
+            const double s = 1.0 / sqrt((double)(L + 1));
+            t.x = 0.0;
+            t.y = -(double)(L + 1) * s;
+            t.z = s;
+            t.w = 0.0;
+        }
+        tab[pos + r] = t;
+    }
+}
+
+__global__ void pack_rho_kernel(const double2 *__restrict__ rho, int64_t ld, int64_t rho_stride, int N,
+                                double2 *__restrict__ cs, int64_t cs_stride)
+{
+    const int K = blockIdx.x + 2;
+    const double2 *R = rho + (int64_t)blockIdx.y * rho_stride;
+    double2 *C = cs + (int64_t)blockIdx.y * cs_stride;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double2 v = R[N - 1];
+        C[0] = make_double2(2.0 * v.x, 2.0 * v.y);
+    }
+    if (K > N) return;
+    const int L = N - K;
+    const double f = (L == 0) ? 1.0 : 2.0;
+    const int64_t pos = diag_pos(K);
+    for (int r = threadIdx.x; r <= K; r += blockDim.x) {
+        double2 v = make_double2(0.0, 0.0);
+        if (r < K) {
+            const int j = K - 1 - r;
+            const double2 e = R[(int64_t)j * ld + j + L];
+            v = make_double2(f * e.x, f * e.y);
+        }
+        C[pos + r] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tile scheduler: persistent CTAs grab `grab` consecutive tiles at a time from a global counter;
+// the last CTA to leave resets the counters so the same slot can serve the next launch.
+// ------------------------------------------------------------------------------------------------
+struct TileCursor {
+    int cur, end;
+};
+
+__device__ __forceinline__ int next_tile(const WigParams &p, TileCursor &tc, int *slot)
+{
+    if (tc.cur < tc.end) return tc.cur++;
+    __syncthreads();
+    if (threadIdx.x == 0) *slot = (int)atomicAdd(&p.ctr[0], (unsigned int)p.grab);
+    __syncthreads();
+    const int base = *slot;
+    if (base >= p.total_tiles) return -1;
+    tc.cur = base + 1;
+    tc.end = min(base + p.grab, p.total_tiles);
+    return base;
+}
+
+__device__ __forceinline__ void leave_grid(const WigParams &p)
+{
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(&p.ctr[1], 1u);
+        if (done == gridDim.x - 1) {
+            p.ctr[0] = 0u;
+            p.ctr[1] = 0u;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-thread point state
+// ------------------------------------------------------------------------------------------------
+template <int PTS>
+struct Points {
+    double ar[PTS], B[PTS];
+    double y0r[PTS], y0i[PTS], y1r[PTS], y1i[PTS];
+    double wr[PTS], wi[PTS];
+    double ai;
+};
+
+template <int PTS>
+__device__ __forceinline__ void clenshaw_step(Points<PTS> &s, const double2 c, const double4 t)
+{
+#pragma unroll
+    for (int p = 0; p < PTS; ++p) {
+        const double tn = fma(s.B[p], t.z, t.y);  // -((L+2k-1) - B)/sqrt((L+k)k)
+        const double n0r = fma(t.x, s.y1r[p], c.x);
+        const double n0i = fma(t.x, s.y1i[p], c.y);
+        const double n1r = fma(tn, s.y1r[p], s.y0r[p]);
+        const double n1i = fma(tn, s.y1i[p], s.y0i[p]);
+        s.y0r[p] = n0r;
+        s.y0i[p] = n0i;
+        s.y1r[p] = n1r;
+        s.y1i[p] = n1i;
+    }
+}
+
+// S_L = y0 - y1 ((L+1) - B)/sqrt(L+1);   w0 <- S_L + w0 * A2 / sqrt(L+1)
+template <int PTS>
+__device__ __forceinline__ void horner_tail(Points<PTS> &s, const double4 t)
+{
+#pragma unroll
+    for (int p = 0; p < PTS; ++p) {
+        const double tn = fma(s.B[p], t.z, t.y);
+        const double Sr = fma(tn, s.y1r[p], s.y0r[p]);
+        const double Si = fma(tn, s.y1i[p], s.y0i[p]);
+        const double ur = s.wr[p] * t.z, ui = s.wi[p] * t.z;
+        s.wr[p] = fma(-ui, s.ai, fma(ur, s.ar[p], Sr));
+        s.wi[p] = fma(ui, s.ar[p], fma(ur, s.ai, Si));
+    }
+}
+
+template <int PTS>
+__device__ __forceinline__ void load_points(const WigParams &p, int q, Points<PTS> &s, int &iy, int &ix0)
+{
+    iy = q / p.chunks_per_row;
+    ix0 = (q - iy * p.chunks_per_row) * PTS;
+    const int iyc = min(iy, p.ny - 1);
+    s.ai = p.g * __ldg(p.yvec + iyc);
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) {
+        const int ixc = min(ix0 + k, p.nx - 1);
+        s.ar[k] = p.g * __ldg(p.xvec + ixc);
+        s.B[k] = fma(s.ar[k], s.ar[k], s.ai * s.ai);
+    }
+}
+
+template <int PTS>
+__device__ __forceinline__ void store_points(const WigParams &p, int frame, int iy, int ix0, const Points<PTS> &s)
+{
+    if (iy >= p.ny) return;
+    double v[PTS];
+#pragma unroll
+    for (int k = 0; k < PTS; ++k) v[k] = s.wr[k] * exp(-0.5 * s.B[k]) * p.scale;
+    double *dst = p.W + (int64_t)frame * p.w_stride + (int64_t)iy * p.nx + ix0;
+    if (p.vec_ok) {  // nx % PTS == 0 and 16-byte aligned rows: every chunk is full
+        if constexpr (PTS % 2 == 0) {
+#pragma unroll
+            for (int k = 0; k < PTS; k += 2) __stcs(reinterpret_cast<double2 *>(dst + k), make_double2(v[k], v[k + 1]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) __stcs(dst + k, v[k]);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < PTS; ++k)
+            if (ix0 + k < p.nx) __stcs(dst + k, v[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// N <= 64: coefficient stream resident in shared memory
+// ------------------------------------------------------------------------------------------------
+template <int PTS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) wigner_resident_kernel(const WigParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)p.R_tot * 32);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.R_tot * 48);
+    int *slot = reinterpret_cast<int *>(bar + 1);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    int loaded_frame = -1;
+    TileCursor tc{0, 0};
+    const int N = p.N;
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        if (frame != loaded_frame) {
+            __syncthreads();  // every warp is done reading the previous frame's coefficients
+            if (tid == 0) {
+                const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
+                const bool first = loaded_frame < 0;
+                mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
+                if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
+                bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            loaded_frame = frame;
+        }
+
+        Points<PTS> s;
+        int iy, ix0;
+        load_points<PTS>(p, tif * THREADS + tid, s, iy, ix0);
+        {
+            const double2 h = cs_s[0];
+#pragma unroll
+            for (int k = 0; k < PTS; ++k) {
+                s.wr[k] = h.x;
+                s.wi[k] = h.y;
+            }
+        }
+        int pos = 1;
+        for (int K = 2; K <= N; ++K) {
+            {
+                const double2 c1 = cs_s[pos], c0 = cs_s[pos + 1];
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) {
+                    s.y1r[k] = c1.x;
+                    s.y1i[k] = c1.y;
+                    s.y0r[k] = c0.x;
+                    s.y0i[k] = c0.y;
+                }
+            }
+            const double2 *cp = cs_s + pos + 2;
+            const double4 *tp = tab_s + pos + 2;
+            const int m = K - 2;
+            int r = 0;
+            for (; r + 1 < m; r += 2) {
+                clenshaw_step<PTS>(s, cp[r], tp[r]);
+                clenshaw_step<PTS>(s, cp[r + 1], tp[r + 1]);
+            }
+            if (r < m) clenshaw_step<PTS>(s, cp[r], tp[r]);
+            horner_tail<PTS>(s, tab_s[pos + K]);
+            pos += K + 1;
+        }
+        store_points<PTS>(p, frame, iy, ix0, s);
+    }
+    leave_grid(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// N > 64: coefficient stream pulled through a shared-memory ring by bulk copies
+// ------------------------------------------------------------------------------------------------
+template <int PTS, int THREADS, int STAGES, int CHUNK>
+__global__ void __launch_bounds__(THREADS, 2) wigner_stream_kernel(const WigParams p)
+{
+    constexpr int NWARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)STAGES * CHUNK * 32);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * CHUNK * 48);
+    uint64_t *empty = full + STAGES;
+    int *slot = reinterpret_cast<int *>(empty + STAGES);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int n_chunks = (p.R_tot + CHUNK - 1) / CHUNK;
+    uint32_t gc = 0;  // chunks this CTA has gone through so far (uniform across the CTA)
+    TileCursor tc{0, 0};
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
+
+        auto produce = [&](uint32_t G, int ci) {
+            const uint32_t st = G % STAGES, use = G / STAGES;
+            mbar_wait(&empty[st], (use & 1u) ^ 1u);
+            const int recs = min(CHUNK, p.R_tot - ci * CHUNK);
+            mbar_arrive_expect_tx(&full[st], (uint32_t)recs * 48u);
+            bulk_g2s(tab_s + (size_t)st * CHUNK, p.tab + (int64_t)ci * CHUNK, (uint32_t)recs * 32u, &full[st]);
+            bulk_g2s(cs_s + (size_t)st * CHUNK, cs_g + (int64_t)ci * CHUNK, (uint32_t)recs * 16u, &full[st]);
+        };
+        if (tid == 0) {
+            const int pre = min(STAGES - 1, n_chunks);
+            for (int d = 0; d < pre; ++d) produce(gc + d, d);
+        }
+
+        Points<PTS> s;
+        int iy, ix0;
+        load_points<PTS>(p, tif * THREADS + tid, s, iy, ix0);
+        int K = 2, rem = 2;
+#pragma unroll
+        for (int k = 0; k < PTS; ++k) s.y0r[k] = s.y0i[k] = s.y1r[k] = s.y1i[k] = 0.0;
+
+        for (int ci = 0; ci < n_chunks; ++ci) {
+            const uint32_t G = gc + ci, st = G % STAGES, use = G / STAGES;
+            mbar_wait(&full[st], use & 1u);
+            const double2 *cp = cs_s + (size_t)st * CHUNK;
+            const double4 *tp = tab_s + (size_t)st * CHUNK;
+            const int nrec = min(CHUNK, p.R_tot - ci * CHUNK);
+            int r = 0;
+            if (ci == 0) {
+                const double2 h = cp[0];
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) {
+                    s.wr[k] = h.x;
+                    s.wi[k] = h.y;
+                }
+                r = 1;
+            }
+            while (r < nrec) {
+                if (rem > 0) {
+                    const int m = min(rem, nrec - r);
+                    const double2 *c = cp + r;
+                    const double4 *t = tp + r;
+                    int i = 0;
+                    for (; i + 1 < m; i += 2) {
+                        clenshaw_step<PTS>(s, c[i], t[i]);
+                        clenshaw_step<PTS>(s, c[i + 1], t[i + 1]);
+                    }
+                    if (i < m) clenshaw_step<PTS>(s, c[i], t[i]);
+                    r += m;
+                    rem -= m;
+                } else {
+                    horner_tail<PTS>(s, tp[r]);
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k) s.y0r[k] = s.y0i[k] = s.y1r[k] = s.y1i[k] = 0.0;
+                    ++r;
+                    ++K;
+                    rem = K;
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+            if (tid == 0 && ci + STAGES - 1 < n_chunks) produce(G + STAGES - 1, ci + STAGES - 1);
+        }
+        gc += (uint32_t)n_chunks;
+        store_points<PTS>(p, frame, iy, ix0, s);
+    }
+    leave_grid(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t launch_build_tab(double4 *tab, int N, cudaStream_t st)
+{
+    build_tab_kernel<<<max(1, N - 1), 128, 0, st>>>(tab, N);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, int N, int batch, double2 *cs,
+                            int64_t cs_stride, cudaStream_t st)
+{
+    dim3 grid(max(1, N - 1), batch);
+    pack_rho_kernel<<<grid, 128, 0, st>>>(rho, ld, rho_stride, N, cs, cs_stride);
+    return cudaGetLastError();
+}
+
+namespace {
+
+constexpr int kStages = 4, kChunk = 256;
+
+template <typename Kern>
+cudaError_t run(Kern kern, int slot, int threads, size_t smem, WigParams &p, int pts, DeviceInfo &dev,
+                cudaStream_t st, int *launches)
+{
+    cudaError_t e;
+    if (!dev.configured[slot]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.smem_optin);
+        if (e != cudaSuccess) return e;
+        dev.configured[slot] = true;
+    }
+    if (dev.occ[slot] == 0 || dev.occ_smem[slot] != smem) {
+        int occ = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
+        dev.occ[slot] = occ;
+        dev.occ_smem[slot] = smem;
+    }
+    p.chunks_per_row = (p.nx + pts - 1) / pts;
+    const int64_t chunks = (int64_t)p.chunks_per_row * p.ny;
+    const int64_t tpf = (chunks + threads - 1) / threads;
+    if (tpf * p.batch > 0x7fffffffLL) return cudaErrorInvalidValue;
+    p.tiles_per_frame = (int)tpf;
+    p.total_tiles = (int)(tpf * p.batch);
+    p.vec_ok = (p.nx % pts == 0) && (((uintptr_t)p.W % 16u) == 0) && (pts % 2 == 0);
+    const int resident = dev.occ[slot] * dev.sm_count;
+    const int grid = (int)min((int64_t)resident, (int64_t)p.total_tiles);
+    p.grab = max(1, p.total_tiles / (grid * 8));
+    kern<<<grid, threads, smem, st>>>(p);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Chooses the tile shape so that small grids still cover every SM, then launches.
+cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches)
+{
+    const int64_t points = (int64_t)p.nx * p.ny * p.batch;
+    if (points == 0) return cudaSuccess;
+    const int64_t want = 2LL * dev.sm_count;  // tiles needed before the big tile pays off
+    if (p.N <= kResidentMaxN) {
+        const size_t smem = (size_t)p.R_tot * 48 + 64;
+        if (points / (256 * 4) >= 2 * want)
+            return run(wigner_resident_kernel<4, 256, 2>, 0, 256, smem, p, 4, dev, st, launches);
+        if (points / (128 * 2) >= 2 * want)
+            return run(wigner_resident_kernel<2, 128, 4>, 1, 128, smem, p, 2, dev, st, launches);
+        return run(wigner_resident_kernel<1, 128, 4>, 2, 128, smem, p, 1, dev, st, launches);
+    }
+    const size_t smem = (size_t)kStages * kChunk * 48 + 2 * kStages * 8 + 64;
+    if (points / (256 * 4) >= want)
+        return run(wigner_stream_kernel<4, 256, kStages, kChunk>, 3, 256, smem, p, 4, dev, st, launches);
+    return run(wigner_stream_kernel<2, 128, kStages, kChunk>, 4, 128, smem, p, 2, dev, st, launches);
+}
+
+}  // namespace bq

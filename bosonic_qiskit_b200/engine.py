@@ -1,0 +1,352 @@
+"""Thin object wrapper over the C ABI: one ``Engine`` per GPU.
+
+NumPy in / NumPy out goes through the ``*_host`` entry points (host buffers,
+staging inside the library); ``torch`` CUDA tensors go through the ``*_dev``
+entry points and stay on the device.  torch is imported lazily and only used
+for device memory and streams.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+import threading
+import weakref
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import BQError, check
+
+METHODS = {"clenshaw": 0, "iterative": 1, "laguerre": 2, "fft": 3}
+
+
+def method_code(method: str) -> int:
+    try:
+        return METHODS[method]
+    except (KeyError, TypeError):
+        # same exception type / text qutip.wigner raises for an unknown method
+        raise TypeError("method must be either 'iterative', 'laguerre', 'fft' or 'clenshaw'.") from None
+
+
+def _c128(a, copy=False) -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=np.complex128)
+    return out.copy() if copy and out is a else out
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _int_array(v: Sequence[int]):
+    arr = (ctypes.c_int * max(len(v), 1))(*[int(x) for x in v])
+    return arr
+
+
+def _n_qubits(dim: int) -> int:
+    n = int(dim).bit_length() - 1
+    if dim <= 0 or (1 << n) != dim:
+        raise ValueError(f"dimension {dim} is not a power of two")
+    return n
+
+
+class Engine:
+    """Owns a ``bq_handle_t`` on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        check(self._lib.bq_create(ctypes.byref(h), int(device)))
+        self._h = h
+        self.device = int(device)
+        self._finalizer = weakref.finalize(self, self._lib.bq_destroy, h)
+
+    def close(self) -> None:
+        self._finalizer()
+
+    # ------------------------------------------------------------------ bookkeeping
+    @property
+    def launches(self) -> int:
+        n = ctypes.c_uint64()
+        check(self._lib.bq_launch_count(self._h, ctypes.byref(n)))
+        return int(n.value)
+
+    def synchronize(self) -> None:
+        check(self._lib.bq_synchronize(self._h))
+
+    def last_device_ms(self) -> float:
+        ms = ctypes.c_double()
+        check(self._lib.bq_last_device_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def fp64_peak_tflops(self, seconds: float = 0.5) -> float:
+        v = ctypes.c_double()
+        check(self._lib.bq_fp64_peak(self._h, float(seconds), ctypes.byref(v)))
+        return float(v.value)
+
+    def profile(self, on: bool) -> None:
+        """Bracket every Wigner-kernel launch with CUDA events (bench.py's roofline leg)."""
+        check(self._lib.bq_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self) -> tuple[float, int]:
+        """(summed kernel ms, launches) since the last read."""
+        ms, n = ctypes.c_double(), ctypes.c_int()
+        check(self._lib.bq_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return float(ms.value), int(n.value)
+
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """NumPy array in page-locked host memory (freed when the array is collected)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        check(self._lib.bq_host_alloc(self._h, nbytes, ctypes.byref(p)))
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
+        weakref.finalize(buf, self._lib.bq_host_free, self._h, p)
+        return arr
+
+    # ------------------------------------------------------------------ partial trace (host)
+    def partial_trace_sv(self, psi, traced: Sequence[int]) -> np.ndarray:
+        """``psi``: (dim,) or (batch, dim) complex -> (D, D) or (batch, D, D)."""
+        psi = _c128(psi)
+        single = psi.ndim == 1
+        psi2 = psi.reshape(1, -1) if single else psi
+        if psi2.ndim != 2:
+            raise ValueError("psi must be 1-D or 2-D")
+        batch, dim = psi2.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        D = 1 << (n - len(traced)) if len(traced) <= n else 0
+        out = np.empty((batch, max(D, 0), max(D, 0)), dtype=np.complex128)
+        check(self._lib.bq_partial_trace_sv_host(self._h, _ptr(psi2), n, _int_array(traced), len(traced), batch, dim,
+                                                 _ptr(out)))
+        return out[0] if single else out
+
+    def partial_trace_sv_multi(self, psi, traced_sets: Sequence[Sequence[int]]) -> np.ndarray:
+        """Several traces of one statevector (all sets the same length) -> (n_sets, D, D)."""
+        psi = _c128(psi).reshape(-1)
+        n = _n_qubits(psi.shape[0])
+        sets = [list(s) for s in traced_sets]
+        if not sets:
+            return np.empty((0, 0, 0), dtype=np.complex128)
+        nt = len(sets[0])
+        if any(len(s) != nt for s in sets):
+            raise ValueError("all traced sets must have the same length")
+        D = 1 << (n - nt) if nt <= n else 0
+        out = np.empty((len(sets), D, D), dtype=np.complex128)
+        flat = [q for s in sets for q in s]
+        check(self._lib.bq_partial_trace_sv_multi_host(self._h, _ptr(psi), n, _int_array(flat), nt, len(sets),
+                                                       _ptr(out)))
+        return out
+
+    def partial_trace_dm(self, rho, traced: Sequence[int]) -> np.ndarray:
+        rho = _c128(rho)
+        single = rho.ndim == 2
+        rho3 = rho.reshape(1, *rho.shape) if single else rho
+        if rho3.ndim != 3 or rho3.shape[1] != rho3.shape[2]:
+            raise ValueError("rho must be (F, F) or (batch, F, F)")
+        batch, F, _ = rho3.shape
+        n = _n_qubits(F)
+        traced = list(traced)
+        D = 1 << (n - len(traced)) if len(traced) <= n else 0
+        out = np.empty((batch, D, D), dtype=np.complex128)
+        check(self._lib.bq_partial_trace_dm_host(self._h, _ptr(rho3), n, _int_array(traced), len(traced), batch,
+                                                 _ptr(out)))
+        return out[0] if single else out
+
+    def photon_number(self, rho) -> np.ndarray:
+        """Unrounded complex <n> per density matrix: (D, D) -> scalar, (batch, D, D) -> (batch,)."""
+        rho = _c128(rho)
+        single = rho.ndim == 2
+        rho3 = rho.reshape(1, *rho.shape) if single else rho
+        batch, D, _ = rho3.shape
+        out = np.empty((batch,), dtype=np.complex128)
+        check(self._lib.bq_photon_number_host(self._h, _ptr(rho3), D, batch, _ptr(out)))
+        return out[0] if single else out
+
+    # ------------------------------------------------------------------ Wigner (host)
+    def wigner(self, rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", out=None) -> np.ndarray:
+        """``rho``: (N, N) or (batch, N, N) -> W (ny, nx) or (batch, ny, nx), indexed [iy, ix]."""
+        code = method_code(method)
+        rho = _c128(rho)
+        single = rho.ndim == 2
+        rho3 = rho.reshape(1, *rho.shape) if single else rho
+        if rho3.ndim != 3 or rho3.shape[1] != rho3.shape[2]:
+            raise TypeError("Input state is not a valid operator.")
+        batch, N, _ = rho3.shape
+        xvec = _f64(xvec).reshape(-1)
+        yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
+        shape = (batch, len(yvec), len(xvec))
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape / dtype / layout")
+        check(self._lib.bq_wigner_host(self._h, _ptr(rho3), N, N, N * N, batch, _ptr(xvec), len(xvec), _ptr(yvec),
+                                       len(yvec), float(g), code, _ptr(out)))
+        return out[0] if single else out
+
+    def state_to_wigner(self, psi, traced: Sequence[int], xvec, yvec=None, g: float = math.sqrt(2),
+                        method: str = "clenshaw", return_rho: bool = False, out=None):
+        """Fused frame loop: ``psi`` (dim,) or (frames, dim) -> W (and optionally the reduced rho)."""
+        code = method_code(method)
+        psi = _c128(psi)
+        single = psi.ndim == 1
+        psi2 = psi.reshape(1, -1) if single else psi
+        batch, dim = psi2.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        xvec = _f64(xvec).reshape(-1)
+        yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
+        shape = (batch, len(yvec), len(xvec))
+        if out is None:
+            out = np.empty(shape, dtype=np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape / dtype / layout")
+        D = 1 << max(n - len(traced), 0)
+        rho = np.empty((batch, D, D), dtype=np.complex128) if return_rho else None
+        check(self._lib.bq_state_to_wigner_host(
+            self._h, _ptr(psi2), n, _int_array(traced), len(traced), batch, dim, _ptr(xvec), len(xvec), _ptr(yvec),
+            len(yvec), float(g), code, _ptr(out), _ptr(rho) if return_rho else None))
+        W = out[0] if single else out
+        if return_rho:
+            return W, (rho[0] if single else rho)
+        return W
+
+    # ------------------------------------------------------------------ device-resident (torch tensors)
+    @staticmethod
+    def _stream_ptr(stream):
+        import torch
+
+        s = torch.cuda.current_stream() if stream is None else stream
+        return ctypes.c_void_p(s.cuda_stream)
+
+    def _check_tensor(self, t, dtype, name):
+        import torch
+
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device.index != self.device:
+            raise ValueError(f"{name} must be a CUDA tensor on device {self.device}")
+        if t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous {dtype}")
+
+    def wigner_t(self, rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", out=None, stream=None):
+        """Device-resident Wigner: rho (batch, N, N) complex128 CUDA tensor -> (batch, ny, nx) float64 tensor."""
+        import torch
+
+        code = method_code(method)
+        self._check_tensor(rho, torch.complex128, "rho")
+        single = rho.dim() == 2
+        rho3 = rho.unsqueeze(0) if single else rho
+        batch, N, _ = rho3.shape
+        yvec = xvec if yvec is None else yvec
+        self._check_tensor(xvec, torch.float64, "xvec")
+        self._check_tensor(yvec, torch.float64, "yvec")
+        if out is None:
+            out = torch.empty((batch, yvec.numel(), xvec.numel()), dtype=torch.float64, device=rho.device)
+        else:
+            self._check_tensor(out, torch.float64, "out")
+        check(self._lib.bq_wigner_dev(self._h, ctypes.c_void_p(rho3.data_ptr()), N, N, N * N, batch,
+                                      ctypes.c_void_p(xvec.data_ptr()), xvec.numel(),
+                                      ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g), code,
+                                      ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+        return out[0] if single else out
+
+    def partial_trace_sv_t(self, psi, traced: Sequence[int], out=None, stream=None):
+        import torch
+
+        self._check_tensor(psi, torch.complex128, "psi")
+        single = psi.dim() == 1
+        psi2 = psi.unsqueeze(0) if single else psi
+        batch, dim = psi2.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        D = 1 << max(n - len(traced), 0)
+        if out is None:
+            out = torch.empty((batch, D, D), dtype=torch.complex128, device=psi.device)
+        check(self._lib.bq_partial_trace_sv_dev(self._h, ctypes.c_void_p(psi2.data_ptr()), n, _int_array(traced),
+                                                len(traced), batch, dim, ctypes.c_void_p(out.data_ptr()),
+                                                self._stream_ptr(stream)))
+        return out[0] if single else out
+
+    def state_to_wigner_t(self, psi, traced: Sequence[int], xvec, yvec=None, g: float = math.sqrt(2),
+                          method: str = "clenshaw", out=None, rho_out=None, stream=None):
+        """Device-resident fused frame loop; ``out`` may alias peer memory opened with ``ipc_open``."""
+        import torch
+
+        code = method_code(method)
+        self._check_tensor(psi, torch.complex128, "psi")
+        single = psi.dim() == 1
+        psi2 = psi.unsqueeze(0) if single else psi
+        batch, dim = psi2.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        yvec = xvec if yvec is None else yvec
+        self._check_tensor(xvec, torch.float64, "xvec")
+        self._check_tensor(yvec, torch.float64, "yvec")
+        out_ptr = None
+        if out is None:
+            out = torch.empty((batch, yvec.numel(), xvec.numel()), dtype=torch.float64, device=psi.device)
+            out_ptr = out.data_ptr()
+        elif isinstance(out, int):
+            out_ptr = out  # raw device pointer (e.g. a peer buffer)
+        else:
+            out_ptr = out.data_ptr()
+        check(self._lib.bq_state_to_wigner_dev(
+            self._h, ctypes.c_void_p(psi2.data_ptr()), n, _int_array(traced), len(traced), batch, dim,
+            ctypes.c_void_p(xvec.data_ptr()), xvec.numel(), ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g),
+            code, ctypes.c_void_p(out_ptr), ctypes.c_void_p(rho_out.data_ptr()) if rho_out is not None else None,
+            self._stream_ptr(stream)))
+        if isinstance(out, int):
+            return None
+        return out[0] if single else out
+
+    def frame_minmax_t(self, W, stream=None):
+        import torch
+
+        self._check_tensor(W, torch.float64, "W")
+        batch = W.shape[0]
+        points = W[0].numel() if batch else 0
+        out = torch.empty((batch, 2), dtype=torch.float64, device=W.device)
+        check(self._lib.bq_frame_minmax_dev(self._h, ctypes.c_void_p(W.data_ptr()), points, batch,
+                                            ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+        return out
+
+    # ------------------------------------------------------------------ CUDA IPC
+    def ipc_export(self, tensor) -> bytes:
+        buf = (ctypes.c_ubyte * 64)()
+        check(self._lib.bq_ipc_export(self._h, ctypes.c_void_p(tensor.data_ptr()), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        p = ctypes.c_void_p()
+        check(self._lib.bq_ipc_open(self._h, buf, ctypes.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, ptr: int) -> None:
+        check(self._lib.bq_ipc_close(self._h, ctypes.c_void_p(ptr)))
+
+
+_engines: dict[int, Engine] = {}
+_engines_lock = threading.Lock()
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine for ``device`` (default: LOCAL_RANK if set, else 0).  Raises without a GPU."""
+    import os
+
+    if device is None:
+        device = int(os.environ.get("BQ_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+    with _engines_lock:
+        eng = _engines.get(device)
+        if eng is None:
+            eng = Engine(device)
+            _engines[device] = eng
+        return eng
+
+
+__all__ = ["Engine", "get_engine", "BQError", "method_code", "METHODS"]

@@ -1,0 +1,220 @@
+"""Drop-in for the Wigner entry points of ``bosonic_qiskit.wigner``.
+
+Same names, keyword arguments, defaults and return layout (``W[iy, ix]`` float64) as the
+reference (``src/bosonic_qiskit/wigner.py:26-190``).  The delegation
+``qutip.wigner(psi=Qobj(rho), xvec, yvec, g, method)`` at ``wigner.py:190`` is replaced by the
+sm_100a Clenshaw kernel (K3, ``csrc/wigner_kernels.cu``); the per-frame loop at
+``wigner.py:92-96`` becomes one fused, batched launch.  ``util.simulate`` (Aer) is untouched and is
+imported from the reference package when a circuit has to be simulated.
+
+Quirks of the reference that are kept on purpose:
+  * ``wigner()`` on a raw 1-D array forms ``np.outer(state, state)`` WITHOUT conjugation
+    (``wigner.py:130-131``);
+  * ``_wigner`` evaluates ``if not yvec`` (``wigner.py:187``), so ``yvec`` is effectively ``xvec``;
+  * several kept qumodes are fed to the Wigner routine as ONE mode of dimension ``cutoff**M``.
+"""
+
+from __future__ import annotations
+
+from typing import Literal, Sequence
+
+import numpy as np
+
+from ._compat import DensityMatrix, Statevector, is_density_matrix, is_statevector
+from .engine import get_engine, method_code
+from .util import _find_qubit_indices, trace_out_qubits
+
+# Available method names in Qutip (wigner.py:22-23)
+WignerMethods = Literal["clenshaw", "iterative", "laguerre", "fft"]
+WignerResult = tuple[np.ndarray, ...]
+
+_SQRT2 = np.sqrt(2)
+
+# test seam: replaced by tests that have no qiskit-aer; None => the reference's own simulate()
+_simulate_impl = None
+
+
+def _simulate(*args, **kwargs):
+    if _simulate_impl is not None:
+        return _simulate_impl(*args, **kwargs)
+    try:
+        from bosonic_qiskit.util import simulate  # the reference package, unchanged
+    except Exception as exc:  # pragma: no cover - needs qiskit + qiskit-aer
+        raise RuntimeError(
+            "simulating a circuit needs the reference package `bosonic_qiskit` (qiskit + qiskit-aer); "
+            "only the trace + Wigner stages run on the GPU"
+        ) from exc
+    return simulate(*args, **kwargs)
+
+
+def _check_fft(method):
+    if method_code(method) == 3:
+        raise NotImplementedError(
+            "method='fft' (qutip._wigner_fourier: eigendecomposition + FFT on its own p-axis) is not "
+            "provided by the B200 path; use 'clenshaw', 'iterative' or 'laguerre'"
+        )
+
+
+def simulate_wigner(
+    circuit,
+    xvec: np.ndarray,
+    shots: int,
+    noise_passes=None,
+    conditional_state: str | None = None,
+    trace: bool = False,
+    method: WignerMethods = "clenshaw",
+    g: float = _SQRT2,
+):
+    """Simulate the circuit, optionally trace out the qubits, and compute the Wigner function
+    (``wigner.py:26-71``).  Returns ``(W, statevector)``."""
+    states, _, _ = _simulate(
+        circuit,
+        shots=shots,
+        noise_passes=noise_passes,
+        conditional_state_vector=True if conditional_state else False,
+        return_fockcounts=False,
+    )
+    if not states:
+        raise RuntimeError("No state vector returned from the simulation")
+
+    state = states[conditional_state] if conditional_state else states
+    _check_fft(method)
+    traced = _find_qubit_indices(circuit) if trace else []
+    xvec = np.asarray(xvec, dtype=np.float64)
+    W = get_engine().state_to_wigner(np.asarray(state.data), traced, xvec, None, g=g, method=method)
+    return W, state
+
+
+def simulate_wigner_multiple_statevectors(
+    circuit,
+    xvec,
+    shots: int,
+    statevector_label: str,
+    num_statevectors: int,
+    noise_passes=None,
+    trace: bool = False,
+    g: float = _SQRT2,
+    method: WignerMethods = "clenshaw",
+) -> list:
+    """One simulation, then trace + Wigner on every saved statevector ``{label}{k}``
+    (``wigner.py:74-98``).  The frame loop is a single batched GPU call."""
+    state, result, _ = _simulate(circuit, shots=shots, noise_passes=noise_passes)
+    if not result.results:
+        raise RuntimeError("No statevector was returned from simulation.")
+
+    data = result.data()
+    frames = [np.asarray(getattr(data[f"{statevector_label}{num}"], "data", data[f"{statevector_label}{num}"]))
+              for num in range(num_statevectors)]
+    if not frames:
+        return []
+    _check_fft(method)
+    traced = _find_qubit_indices(circuit) if trace else []
+    W = frames_to_wigner(frames, traced, xvec, g=g, method=method)
+    return [W[k] for k in range(W.shape[0])]
+
+
+def frames_to_wigner(frames, traced: Sequence[int], xvec, g: float = _SQRT2, method: WignerMethods = "clenshaw",
+                     out=None) -> np.ndarray:
+    """Batched body of the reference's frame loops: (F, 2**n) statevectors -> (F, S, S) Wigner grids.
+
+    Replaces ``for num in range(num_statevectors): trace_out_qubits(...); _wigner(...)``
+    (``wigner.py:92-96``, ``animate.py:326-352``) with one call of ``bq_state_to_wigner_host``.
+    """
+    psi = np.ascontiguousarray(np.stack([np.asarray(f, dtype=np.complex128).reshape(-1) for f in frames]))
+    xvec = np.asarray(xvec, dtype=np.float64)
+    return get_engine().state_to_wigner(psi, list(traced), xvec, None, g=g, method=method, out=out)
+
+
+def wigner(
+    state,
+    axes_min: int = -6,
+    axes_max: int = 6,
+    axes_steps: int = 200,
+    g: float = _SQRT2,
+    method: WignerMethods = "clenshaw",
+):
+    """Wigner function of a state on ``linspace(axes_min, axes_max, axes_steps)**2`` (``wigner.py:101-136``)."""
+    if is_statevector(state):
+        state = DensityMatrix(state)
+
+    if not is_density_matrix(state):
+        state = np.atleast_1d(state)
+
+        # If we have a statevector, turn it into density matrix
+        if state.ndim == 1:
+            state = np.outer(state, state)  # NB: no conjugate, as in the reference (wigner.py:130-131)
+
+        state = DensityMatrix(state)
+
+    xvec = np.linspace(axes_min, axes_max, axes_steps)
+    return _wigner(state, xvec, g=g, method=method)
+
+
+def wigner_mle(
+    states: Sequence,
+    axes_min: int = -6,
+    axes_max: int = 6,
+    axes_steps: int = 200,
+    g: float = _SQRT2,
+    method: WignerMethods = "clenshaw",
+):
+    """Maximum-likelihood (per-amplitude normal fit = mean) state over shots, then its Wigner function
+    (``wigner.py:139-175``).  ``scipy.stats.norm.fit`` returns the sample mean as its location, which
+    is what is computed here directly."""
+    states_data = np.stack([np.asarray(getattr(s, "data", s)) for s in states])
+    mle_state = states_data.mean(axis=0)
+    mle_normalized = mle_state / np.linalg.norm(mle_state)
+    return wigner(mle_normalized, axes_min, axes_max, axes_steps, g=g, method=method)
+
+
+def _wigner(state, xvec, yvec=None, g: float = _SQRT2, method: WignerMethods = "clenshaw"):
+    """``qutip.wigner(Qobj(rho), xvec, yvec, g, method)`` on the GPU (``wigner.py:178-190``)."""
+    rho = np.asarray(state.data)
+
+    if not yvec:  # same truthiness test as the reference (wigner.py:187)
+        yvec = xvec
+
+    _check_fft(method)
+    if rho.ndim == 1:  # qutip turns kets into density matrices
+        rho = np.outer(rho, rho.conj())
+    return get_engine().wigner(rho, np.asarray(xvec, dtype=np.float64), np.asarray(yvec, dtype=np.float64), g=g,
+                               method=method)
+
+
+def plot_wigner(
+    circuit,
+    state_vector,
+    trace: bool = True,
+    file=None,
+    axes_min: int = -6,
+    axes_max: int = 6,
+    axes_steps: int = 200,
+    num_colors: int = 100,
+    draw_grid: bool = False,
+    dpi: int = 100,
+    **wigner_kwargs,
+):
+    """Wigner function of ``state_vector`` (traced to the qumodes by default) handed to the
+    reference's matplotlib ``plot`` (``wigner.py:193-244``).  Rendering stays on the host and is the
+    reference's own code; only the trace + Wigner stages run on the GPU."""
+    state = trace_out_qubits(circuit, state_vector) if trace else DensityMatrix(state_vector)
+    w_fock = wigner(state=state, axes_min=axes_min, axes_max=axes_max, axes_steps=axes_steps, **wigner_kwargs)
+    try:
+        from bosonic_qiskit.wigner import plot  # reference plotting, unchanged
+    except Exception as exc:  # pragma: no cover - needs matplotlib + qiskit
+        raise RuntimeError("plotting needs the reference package `bosonic_qiskit` and matplotlib") from exc
+    plot(data=w_fock, axes_min=axes_min, axes_max=axes_max, axes_steps=axes_steps, file=file, num_colors=num_colors,
+         draw_grid=draw_grid, dpi=dpi)
+
+
+__all__ = [
+    "WignerMethods",
+    "WignerResult",
+    "simulate_wigner",
+    "simulate_wigner_multiple_statevectors",
+    "frames_to_wigner",
+    "wigner",
+    "wigner_mle",
+    "_wigner",
+    "plot_wigner",
+]

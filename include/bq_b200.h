@@ -1,0 +1,155 @@
+/*
+ * bq_b200.h -- C ABI of the B200-native statevector -> reduced rho -> Wigner grid path.
+ *
+ * The reference (C2QA/bosonic-qiskit) has no FFI for this path: the seam is two
+ * Python call sites into third-party libraries,
+ *     qutip.wigner(psi=Qobj(rho), xvec, yvec, g, method)      src/bosonic_qiskit/wigner.py:190
+ *     qiskit.quantum_info.partial_trace(state, qargs)         src/bosonic_qiskit/util.py:580,596,619,693
+ * plus the frame loops that call them once per frame
+ *     src/bosonic_qiskit/wigner.py:92-96, src/bosonic_qiskit/animate.py:180-206,326-352,
+ *     src/bosonic_qiskit/util.py:688-694.
+ * Every entry point below names the seam it replaces.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - complex128 is passed as interleaved (re, im) doubles: `const double *` of 2*count.
+ *   - All functions return 0 on success, a negative bq_status otherwise; the message
+ *     for the calling thread's last failure is bq_last_error().
+ *   - `_host` entry points take HOST pointers, run on the handle's device, and return
+ *     when the outputs are complete in host memory.
+ *   - `_dev` entry points take DEVICE pointers of the handle's device and enqueue on
+ *     `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) without
+ *     synchronising.
+ *   - There is no CPU fallback: without a usable CUDA device bq_create fails.
+ *   - A handle may be used from any host thread, one call at a time.
+ */
+#ifndef BQ_B200_H
+#define BQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BQ_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+typedef enum bq_status {
+    BQ_OK = 0,
+    BQ_ERR_INVALID = -1,  /* bad argument (NULL, negative size, bad qubit index, non power of two ...) */
+    BQ_ERR_CUDA = -2,     /* a CUDA runtime call failed; see bq_last_error() */
+    BQ_ERR_NO_DEVICE = -3,/* no CUDA device / requested ordinal absent */
+    BQ_ERR_UNSUPPORTED = -4 /* e.g. method="fft" */
+} bq_status;
+
+/* qutip.wigner `method=` values (src/bosonic_qiskit/wigner.py:22 WignerMethods).  The three grid
+ * methods are the same function evaluated by different recurrences; this library serves all three
+ * names from the Clenshaw kernel.  "fft" (different p axis) is not implemented: BQ_ERR_UNSUPPORTED. */
+typedef enum bq_wigner_method {
+    BQ_WIGNER_CLENSHAW = 0,
+    BQ_WIGNER_ITERATIVE = 1,
+    BQ_WIGNER_LAGUERRE = 2,
+    BQ_WIGNER_FFT = 3
+} bq_wigner_method;
+
+typedef struct bq_handle_s *bq_handle_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int bq_version(void);
+const char *bq_last_error(void);
+int bq_device_count(int *count);
+int bq_create(bq_handle_t *out, int device);
+int bq_destroy(bq_handle_t h);
+int bq_device(bq_handle_t h, int *device);
+/* kernels this handle has launched since creation (bench.py's gpu_launches) */
+int bq_launch_count(bq_handle_t h, uint64_t *count);
+/* blocks until everything the handle enqueued on its own streams is done */
+int bq_synchronize(bq_handle_t h);
+
+/* ---- pinned host buffers (optional; outputs placed here are written by the GPU directly) ---- */
+int bq_host_alloc(bq_handle_t h, size_t bytes, void **out);
+int bq_host_free(bq_handle_t h, void *ptr);
+
+/* ---- partial trace: replaces qiskit.quantum_info.partial_trace ------------------------------ */
+/* Statevector branch (src/bosonic_qiskit/util.py:580,596,619,693).
+ *   psi      batch statevectors, each 2^n_qubits complex128, `psi_stride` complex elements apart
+ *   traced   n_traced distinct qubit positions (Qiskit little-endian bit index) to sum over
+ *   rho_out  batch x D x D complex128 row-major, D = 2^(n_qubits-n_traced); kept qubits keep
+ *            their significance order.  n_traced == n_qubits gives the 1x1 norm <psi|psi>.        */
+int bq_partial_trace_sv_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                             int batch, int64_t psi_stride, double *rho_out);
+int bq_partial_trace_sv_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                            int batch, int64_t psi_stride, double *d_rho_out, void *stream);
+
+/* Several traces of the SAME statevector in one call: the per-qumode loop of
+ * util.avg_photon_num (src/bosonic_qiskit/util.py:688-694).  `traced` holds n_sets lists of
+ * n_traced positions each (all sets trace the same number of qubits); rho_out is n_sets x D x D. */
+int bq_partial_trace_sv_multi_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced,
+                                   int n_traced, int n_sets, double *rho_out);
+int bq_partial_trace_sv_multi_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced,
+                                  int n_traced, int n_sets, double *d_rho_out, void *stream);
+
+/* DensityMatrix branch: rho_keep[i,j] = sum_t rho[(i,t),(j,t)]  (reached through
+ * cv_partial_trace / avg_photon_num with a DensityMatrix, src/bosonic_qiskit/util.py:619,693).  */
+int bq_partial_trace_dm_host(bq_handle_t h, const double *rho, int n_qubits, const int *traced, int n_traced,
+                             int batch, double *rho_out);
+int bq_partial_trace_dm_dev(bq_handle_t h, const double *d_rho, int n_qubits, const int *traced, int n_traced,
+                            int batch, double *d_rho_out, void *stream);
+
+/* <n> = sum_n n rho_nn / sum_n rho_nn per batch element, unrounded; out[2*b] real, out[2*b+1] imag
+ * (util.qumode_avg_photon_num, src/bosonic_qiskit/util.py:699-736, checks the imaginary part).  */
+int bq_photon_number_host(bq_handle_t h, const double *rho, int D, int batch, double *out);
+int bq_photon_number_dev(bq_handle_t h, const double *d_rho, int D, int batch, double *d_out, void *stream);
+
+/* ---- Wigner grid: replaces qutip.wigner(Qobj(rho), xvec, yvec, g, method) -------------------- */
+/*   rho   batch x N x N complex128, row-major with leading dimension `ld` (complex elements) and
+ *         `rho_stride` complex elements between frames; only the upper triangle is read
+ *   W_out batch x ny x nx float64, W[b][iy][ix]  (src/bosonic_qiskit/wigner.py:178-190)          */
+int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                   const double *xvec, int nx, const double *yvec, int ny, double g, int method,
+                   double *W_out);
+int bq_wigner_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                  const double *d_xvec, int nx, const double *d_yvec, int ny, double g, int method,
+                  double *d_W_out, void *stream);
+
+/* ---- fused frame loop: psi_k -> rho_k -> W_k for a batch of frames --------------------------- */
+/* Replaces the loop bodies at src/bosonic_qiskit/wigner.py:92-96 and animate.py:326-352
+ * (trace_out_qubits + _wigner per frame).  n_traced == 0 means rho_k = |psi_k><psi_k|
+ * (DensityMatrix(state), wigner.py:69,95).  rho_out / d_rho_out may be NULL.                      */
+int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                            int batch, int64_t psi_stride, const double *xvec, int nx, const double *yvec,
+                            int ny, double g, int method, double *W_out, double *rho_out);
+int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                           int batch, int64_t psi_stride, const double *d_xvec, int nx, const double *d_yvec,
+                           int ny, double g, int method, double *d_W_out, double *d_rho_out, void *stream);
+
+/* per-frame (min, max) of a finished batch of grids: the colour-scale reduction of
+ * animate._animate (src/bosonic_qiskit/animate.py:265-311).  out[2*b] = min, out[2*b+1] = max.    */
+int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, double *d_out,
+                        void *stream);
+
+/* ---- measurement helpers (bench.py only) ----------------------------------------------------- */
+/* Runs a register-resident DFMA loop on every SM and reports the sustained FP64 rate: the
+ * roofline denominator for the Wigner kernel (MEASURED_PEAKS.json has no fp64 entry).           */
+int bq_fp64_peak(bq_handle_t h, double seconds, double *tflops);
+/* device time (ms) the most recent `_host` call spent between its first H2D and last D2H */
+int bq_last_device_ms(bq_handle_t h, double *ms);
+/* When enabled, every launch of the Wigner grid kernel (K3) is bracketed by CUDA events on the
+ * stream it is launched on; bq_profile_read synchronises those streams, returns the summed device
+ * time and the number of launches since the last read, and clears the record.                    */
+int bq_profile_enable(bq_handle_t h, int on);
+int bq_profile_read(bq_handle_t h, double *total_ms, int *launches);
+
+/* ---- CUDA IPC plumbing for the multi-GPU tile gather ---------------------------------------- */
+/* One process per GPU: the root exports its gather buffer, peers open it and let the Wigner
+ * kernel store finished tiles straight into it over NVLink (replaces the pickled return of
+ * multiprocessing.Pool.starmap, src/bosonic_qiskit/animate.py:191-206).  handle64 = 64 bytes.   */
+int bq_ipc_export(bq_handle_t h, void *d_ptr, unsigned char *handle64);
+int bq_ipc_open(bq_handle_t h, const unsigned char *handle64, void **d_ptr);
+int bq_ipc_close(bq_handle_t h, void *d_ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BQ_B200_H */
