@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="leave results sharded (skip the NCCL gather)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--fp64-probe-seconds", type=float, default=1.0, help="length of the DFMA peak probe")
     return ap.parse_args()
 
 
@@ -88,62 +89,88 @@ def describe(wl: dict, world: int) -> dict:
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clock, power and throttle reasons WHILE the timed region runs (NVML, ~2 ms period;
+    falls back to `nvidia-smi -lms` when NVML is not importable)."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines: list[str] = []
+        self.samples: list[tuple[float, float, int]] = []  # (sm MHz, watts, reason bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        watts = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        reasons = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((mhz, watts, reasons))
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._start_smi()
+
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.sw_power_cap,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown")
+        try:
+            self._smi = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+            def pump():
+                bits = [0x8, 0x4, 0x20, 0x40]
+                for line in self._smi.stdout:
+                    parts = [x.strip() for x in line.split(",")]
+                    try:
+                        mask = sum(b for b, v in zip(bits, parts[3:7]) if v.lower().startswith("active"))
+                        self.samples.append((float(parts[0]), float(parts[2]), mask))
+                        self.sm_max = float(parts[1])
+                    except Exception:
+                        continue
+
+            self._thread = threading.Thread(target=pump, daemon=True)
+            self._thread.start()
+        except Exception:
+            self._smi = None
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                power.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        # under load = samples in the upper half of the power range
+        self._stop.set()
+        if self._smi is not None:
+            time.sleep(0.05)
+            self._smi.terminate()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+        sm = [x[0] for x in self.samples]
+        power = [x[1] for x in self.samples]
         thr = 0.5 * (min(power) + max(power))
-        loaded = [s for s, p in zip(sm, power) if p >= thr] or sm
-        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "power_w_max": float(max(power)), "samples": len(sm)}
+        loaded = [m for m, w, _ in self.samples if w >= thr] or sm  # under load = upper half of the power range
+        mask = 0
+        for _, w, r in self.samples:
+            if w >= thr:
+                mask |= r
+        reasons = sorted(k for k, b in self.REASONS.items() if mask & b)
+        return {"sm_mhz": float(np.median(loaded)), "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "power_w_max": float(max(power)), "samples": len(sm), "samples_under_load": len(loaded)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -289,7 +316,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
-    fp64_peak = eng.fp64_peak_tflops(1.0)  # sustained DFMA rate on this GPU, right before the timed region
+    fp64_peak = eng.fp64_peak_tflops(args.fp64_probe_seconds)  # sustained DFMA rate on this GPU, right before the timed region
 
     sampler = ClockSampler(local)
     if rank == 0:

@@ -49,6 +49,8 @@ SIGNATURES = {
     "bq_last_device_ms": (c_int, [_H, _dp]),
     "bq_profile_enable": (c_int, [_H, c_int]),
     "bq_profile_read": (c_int, [_H, _dp, _ip]),
+    "bq_device_alloc": (c_int, [_H, c_size_t, POINTER(c_void_p)]),
+    "bq_device_free": (c_int, [_H, c_void_p]),
     "bq_ipc_export": (c_int, [_H, c_void_p, c_void_p]),
     "bq_ipc_open": (c_int, [_H, c_void_p, POINTER(c_void_p)]),
     "bq_ipc_close": (c_int, [_H, c_void_p]),

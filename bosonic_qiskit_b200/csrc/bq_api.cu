@@ -765,6 +765,7 @@ int bq_fp64_peak(bq_handle_t h, double seconds, double *tflops)
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->dev.device);
     CU(h->small_dev.reserve(64));
+    CU(cudaMemsetAsync(h->small_dev.ptr, 0, 64, h->stream));
     const int grid = h->dev.sm_count * 8;
     const int iters = 4096;
     const double flops_per_launch = (double)grid * 256.0 * iters * 16.0 * 8.0 * 2.0;
@@ -827,6 +828,23 @@ int bq_profile_read(bq_handle_t h, double *total_ms, int *launches)
 }
 
 // ---- CUDA IPC ----------------------------------------------------------------------------------
+int bq_device_alloc(bq_handle_t h, size_t bytes, void **d_ptr)
+{
+    if (!h || !d_ptr) return fail(BQ_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(h->dev.device);
+    CU(cudaMalloc(d_ptr, std::max<size_t>(bytes, 1)));
+    return BQ_OK;
+}
+
+int bq_device_free(bq_handle_t h, void *d_ptr)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (!d_ptr) return BQ_OK;
+    DeviceGuard guard(h->dev.device);
+    CU(cudaFree(d_ptr));
+    return BQ_OK;
+}
+
 int bq_ipc_export(bq_handle_t h, void *d_ptr, unsigned char *handle64)
 {
     if (!h || !d_ptr || !handle64) return fail(BQ_ERR_INVALID, "NULL argument");

@@ -342,22 +342,29 @@ cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, doub
 // ------------------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread, nothing else in the loop body.
 // ------------------------------------------------------------------------------------------------
+// 16 independent accumulators, acc_i = fma(b_i, m, acc_i): two register operands + one warp-uniform
+// operand per DFMA.  This is the fastest DFMA pattern found on B200 (profiles/microbench/dfma_rf.cu:
+// 37.1 TFLOP/s = 99.8 % of 148 SM x 64 FMA/clk x 1.965 GHz); patterns with three distinct register
+// operands run slower, which is a property of the register file, not of the fp64 pipe.
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double *sink, int iters)
 {
-    double a[8];
+    double a[16], b[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
-    const double m = 1.0 - 1e-12, c = 1e-12;
+    for (int i = 0; i < 16; ++i) {
+        a[i] = 1e-9 * (threadIdx.x + i);
+        b[i] = 1.0 + 1e-6 * (threadIdx.x * 16 + i);
+    }
+    const double m = sink[1];  // warp-uniform, unknown at compile time
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = fma(a[i], m, c);
+            for (int i = 0; i < 16; ++i) a[i] = fma(b[i], m, a[i]);
         }
     }
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += a[i];
+    for (int i = 0; i < 16; ++i) s += a[i];
     if (s == 123.456) sink[0] = s;  // never true; keeps the chains alive
 }
 

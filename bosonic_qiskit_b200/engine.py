@@ -316,9 +316,21 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ CUDA IPC
-    def ipc_export(self, tensor) -> bytes:
+    def device_alloc(self, nbytes: int) -> int:
+        """Raw cudaMalloc on this engine's device (whole allocation: exportable through CUDA IPC)."""
+        p = ctypes.c_void_p()
+        check(self._lib.bq_device_alloc(self._h, int(nbytes), ctypes.byref(p)))
+        return int(p.value)
+
+    def device_free(self, ptr: int) -> None:
+        check(self._lib.bq_device_free(self._h, ctypes.c_void_p(ptr)))
+
+    def ipc_export(self, ptr) -> bytes:
+        """64-byte CUDA IPC handle of an allocation made with ``device_alloc`` (or a tensor's storage base)."""
+        if not isinstance(ptr, int):
+            ptr = ptr.data_ptr()
         buf = (ctypes.c_ubyte * 64)()
-        check(self._lib.bq_ipc_export(self._h, ctypes.c_void_p(tensor.data_ptr()), buf))
+        check(self._lib.bq_ipc_export(self._h, ctypes.c_void_p(ptr), buf))
         return bytes(buf)
 
     def ipc_open(self, handle: bytes) -> int:

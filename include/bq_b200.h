@@ -145,6 +145,10 @@ int bq_profile_read(bq_handle_t h, double *total_ms, int *launches);
 /* One process per GPU: the root exports its gather buffer, peers open it and let the Wigner
  * kernel store finished tiles straight into it over NVLink (replaces the pickled return of
  * multiprocessing.Pool.starmap, src/bosonic_qiskit/animate.py:191-206).  handle64 = 64 bytes.   */
+/* plain cudaMalloc / cudaFree on the handle's device: IPC handles name whole allocations, so the
+ * gather buffer must not be a sub-range of a caching allocator's block */
+int bq_device_alloc(bq_handle_t h, size_t bytes, void **d_ptr);
+int bq_device_free(bq_handle_t h, void *d_ptr);
 int bq_ipc_export(bq_handle_t h, void *d_ptr, unsigned char *handle64);
 int bq_ipc_open(bq_handle_t h, const unsigned char *handle64, void **d_ptr);
 int bq_ipc_close(bq_handle_t h, void *d_ptr);

@@ -1,5 +1,7 @@
 """Parity of the CUDA partial-trace kernels (K1 / K2 / K5) with the CPU oracle, through the C ABI."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -31,7 +33,7 @@ def test_sv_vs_oracle(engine, n, traced):
 
 
 def test_notebook_golden(engine):
-    g = np.load("tests/golden/notebook_cutoff4.npz")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_cutoff4.npz"))
     rho = engine.partial_trace_sv(g["psi"], list(g["traced"]))
     assert np.abs(rho - g["rho"]).max() < 2e-8  # the notebook prints 8 digits
 

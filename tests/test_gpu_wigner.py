@@ -3,6 +3,8 @@
 Tolerance (north_star): max|dW| / max|W| <= 1e-10 in fp64.
 """
 
+import os
+
 import numpy as np
 import pytest
 
@@ -162,7 +164,7 @@ def test_only_upper_triangle_is_read(engine):
 
 # ---- BASELINE.json configs ------------------------------------------------------------------
 def test_config1_golden(engine):
-    g = np.load("tests/golden/config1_cat.npz")
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config1_cat.npz"))
     x = np.linspace(-6, 6, 200)
     W, rho = engine.state_to_wigner(g["psi"], list(g["traced"]), x, return_rho=True)
     assert rel_err(rho, g["rho"]) < TOL
