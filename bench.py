@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--frames", type=int, default=None, help="frames per rank (c3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-gather", action="store_true", help="leave results sharded (skip the NCCL gather)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"],
+                    help="N>1: how finished grids reach rank 0 (peer = kernels store into rank 0's buffer over NVLink)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--fp64-probe-seconds", type=float, default=1.0, help="length of the DFMA peak probe")
     return ap.parse_args()
@@ -287,8 +288,15 @@ def main():
     W_t = torch.empty((frames, S, S), dtype=torch.float64, device=dev)
     rho_t = torch.empty((frames, N, N), dtype=torch.complex128, device=dev)
     gathered = None
-    if world > 1 and not args.no_gather:
+    peer = None
+    gather_mode = args.gather if (world > 1 and not multi_sets) else ("nccl" if world > 1 and args.gather != "none" else "none")
+    if world > 1 and gather_mode == "nccl":
         gathered = torch.empty((world * frames, S, S), dtype=torch.float64, device=dev) if rank == 0 else None
+    if world > 1 and gather_mode == "peer":
+        from bosonic_qiskit_b200.parallel import PeerGatherBuffer
+
+        peer = PeerGatherBuffer(eng, (world * frames, S, S), dst=0)  # collective; outside the timed region
+        peer_out = peer.ptr_for(rank * frames)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
 
@@ -304,9 +312,12 @@ def main():
                                                          len(sets[0]), len(sets), ctypes.c_void_p(rho_t.data_ptr()),
                                                          ctypes.c_void_p(stream.cuda_stream)))
             eng.wigner_t(rho_t, x_t, out=W_t)
+        elif peer is not None:
+            # fused compute + gather: the kernel's stores land in rank 0's buffer (NVLink peer memory)
+            eng.state_to_wigner_t(psi_t, wl["traced"], x_t, out=peer_out, rho_out=rho_t)
         else:
             eng.state_to_wigner_t(psi_t, wl["traced"], x_t, out=W_t, rho_out=rho_t)
-        if world > 1 and not args.no_gather:
+        if world > 1 and gather_mode == "nccl":
             if rank == 0:
                 dist.gather(W_t, list(gathered.view(world, frames, S, S).unbind(0)), dst=0)
             else:
@@ -436,7 +447,9 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
-        "gather": None if world == 1 else ("nccl gather to rank 0 inside the step" if not args.no_gather else "none (sharded)"),
+        "gather": None if world == 1 else {"peer": "kernel stores finished tiles into rank 0's buffer over NVLink (CUDA IPC peer memory), inside the step",
+                                             "nccl": "torch.distributed.gather (NCCL) to rank 0 inside the step",
+                                             "none": "none (results stay sharded)"}[gather_mode],
     }
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -764,8 +764,8 @@ int bq_fp64_peak(bq_handle_t h, double seconds, double *tflops)
     if (!h || !tflops) return fail(BQ_ERR_INVALID, "NULL argument");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->dev.device);
-    CU(h->small_dev.reserve(64));
-    CU(cudaMemsetAsync(h->small_dev.ptr, 0, 64, h->stream));
+    CU(h->small_dev.reserve(512));
+    CU(cudaMemsetAsync(h->small_dev.ptr, 0, 512, h->stream));
     const int grid = h->dev.sm_count * 8;
     const int iters = 4096;
     const double flops_per_launch = (double)grid * 256.0 * iters * 16.0 * 8.0 * 2.0;

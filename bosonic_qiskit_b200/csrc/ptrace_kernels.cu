@@ -348,18 +348,19 @@ cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, doub
 // operands run slower, which is a property of the register file, not of the fp64 pipe.
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double *sink, int iters)
 {
-    double a[16], b[16];
+    double a[16], b[16], c[16];
+    const double *in = sink + 2;  // 48 warp-uniform values, unknown at compile time
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        a[i] = 1e-9 * (threadIdx.x + i);
-        b[i] = 1.0 + 1e-6 * (threadIdx.x * 16 + i);
+        a[i] = in[i] + threadIdx.x * 1e-9;
+        b[i] = in[16 + i];
+        c[i] = in[32 + i];
     }
-    const double m = sink[1];  // warp-uniform, unknown at compile time
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = fma(b[i], m, a[i]);
+            for (int i = 0; i < 16; ++i) a[i] = fma(b[i], c[i], a[i]);
         }
     }
     double s = 0.0;

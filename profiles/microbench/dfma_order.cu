@@ -40,6 +40,19 @@ __device__ __forceinline__ void step(const double4 t, const double2 c, const dou
             const double n0i = fma(t.x, y1i[p], c.y);
             y0r[p] = n0r; y0i[p] = n0i; y1r[p] = n1r; y1i[p] = n1i;
         }
+    } else if (ORDER == 3) {
+        // NOT the real recurrence: the third operand of the y1 update is a shared coefficient instead of y0,
+        // so that no DFMA reads more than two per-thread registers.  Same instruction count and mix;
+        // tells how fast the loop would run if the three-register DFMAs were gone.
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double tn = fma(B[p], t.z, t.y);
+            const double n0r = fma(t.x, y0r[p], c.x);
+            const double n0i = fma(t.x, y0i[p], c.y);
+            const double n1r = fma(tn, y1r[p], t.w);
+            const double n1i = fma(tn, y1i[p], t.w);
+            y0r[p] = n0r; y0i[p] = n0i; y1r[p] = n1r; y1i[p] = n1i;
+        }
     } else {
         double tn[P];
 #pragma unroll
@@ -128,5 +141,7 @@ int main()
     run<8, 1, 2>(sms, out, in);
     run<8, 2, 2>(sms, out, in);
     run<6, 2, 2>(sms, out, in);
+    run<4, 3, 4>(sms, out, in);
+    run<8, 3, 2>(sms, out, in);
     return 0;
 }
