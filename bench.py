@@ -187,13 +187,14 @@ def cpu_sample(wl: dict, seconds: float):
     # NumPy cost model from SURVEY 6: ~1 algorithmic GFLOP/s -> rows that fit in `seconds`
     per_row = S * workloads.flops_per_point(N) / 0.9e9
     rows = int(max(1, min(S, seconds / per_row)))
-    ys = x[np.linspace(0, S - 1, rows).astype(int)]
+    idx = np.linspace(0, S - 1, rows + 2).astype(int)[1:-1]  # evenly spaced interior rows
+    ys = x[idx]
     t0 = time.perf_counter()
     rho = partial_trace_sv(psi, traced)
     W = wigner_clenshaw(rho, x, ys)
     dt = time.perf_counter() - t0
     assert W.shape == (rows, S)
-    return rows * S / dt, f"psi->rho->W on {rows} of {S} grid rows x {S} columns, 1 frame, {dt:.1f} s", rho, ys, W
+    return rows * S / dt, f"psi->rho->W on {rows} of {S} grid rows x {S} columns, 1 frame, {dt:.1f} s", rho, idx, W
 
 
 def _ref_worker(args):
@@ -411,6 +412,14 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
 
+    traffic = None  # DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(wl["name"])
+        if t:
+            traffic = {"bytes": t["dram_bytes_read"] + t["dram_bytes_write"], "source": t["source"]}
+    except Exception:
+        pass
     F = workloads.flops_per_point(N)
     kern_avg_ms = kern_ms / max(kern_n, 1)
     achieved_tf = points_rank * F / (kern_avg_ms * 1e-3) / 1e12
@@ -421,7 +430,7 @@ def main():
                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
         "flops_per_point": F, "points_per_launch": points_rank, "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
         "kernel_share_of_step": kern_avg_ms / ms_per_step,
-        "traffic": None,
+        "traffic": traffic,
         "hbm_store": {"bound": "hbm", "achieved": points_rank * 8 / (kern_avg_ms * 1e-3) / 1e9, "peak": hbm_peak,
                       "unit": "GB/s", "peak_source": hbm_src,
                       "frac": points_rank * 8 / (kern_avg_ms * 1e-3) / 1e9 / hbm_peak},
@@ -431,14 +440,13 @@ def main():
     cpu = None
     parity = None
     if not args.no_cpu_baseline and world == 1:
-        v, sample, rho_ref, ys, W_ref = cpu_sample(wl, args.cpu_seconds)
+        v, sample, rho_ref, idx, W_ref = cpu_sample(wl, args.cpu_seconds)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": sample + " (NumPy restatement of qiskit.partial_trace + qutip.wigner clenshaw; "
                                   "qutip/qiskit are not installed)"}
-        idx = np.linspace(0, S - 1, len(ys)).astype(int)
         W_dev = W_t[0].cpu().numpy()[idx]
         rho_dev = rho_t[0].cpu().numpy()
-        parity = {"max_abs_dW_over_max_W": float(np.abs(W_dev - W_ref).max() / np.abs(W_ref).max()),
+        parity = {"max_abs_dW_over_max_W": float(np.abs(W_dev - W_ref).max() / float(W_t[0].abs().max().item())),
                   "max_abs_drho_over_max_rho": float(np.abs(rho_dev - rho_ref).max() / np.abs(rho_ref).max()),
                   "tolerance": 1e-10}
 

@@ -319,6 +319,20 @@ int check_trace_args(const void *psi, int n_qubits, int n_traced, int batch, int
     return BQ_OK;
 }
 
+// If `p` is page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister under
+// UVA), returns the device-side alias: kernels then store results straight into host memory over PCIe
+// (posted writes that overlap the fp64 math) and the separate D2H copy disappears.
+double *mapped_alias(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (attr.type == cudaMemoryTypeHost && attr.devicePointer) return (double *)attr.devicePointer;
+    return nullptr;
+}
+
 struct HostTimer {
     bq_handle_t h;
     explicit HostTimer(bq_handle_t hh) : h(hh) { cudaEventRecord(h->ev_t0, h->stream); }
@@ -657,13 +671,17 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
     const size_t in_elems = (size_t)((int64_t)(batch - 1) * rho_stride + (int64_t)(N - 1) * ld + N);
     const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
     CU(h->in_dev.reserve(in_elems * sizeof(double2)));
-    CU(h->out_dev.reserve(out_b));
+    double *d_out = mapped_alias(W_out);
+    const bool direct = d_out != nullptr;
+    if (!direct) {
+        CU(h->out_dev.reserve(out_b));
+        d_out = (double *)h->out_dev.ptr;
+    }
     HostTimer timer(h);
     CU(cudaMemcpyAsync(h->in_dev.ptr, rho, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-    rc = wigner_core(h, (const double2 *)h->in_dev.ptr, N, ld, rho_stride, batch, dx, nx, dy, ny, g,
-                     (double *)h->out_dev.ptr, h->stream);
+    rc = wigner_core(h, (const double2 *)h->in_dev.ptr, N, ld, rho_stride, batch, dx, nx, dy, ny, g, d_out, h->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    if (!direct) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
     return timer.finish();
 }
 
@@ -727,15 +745,20 @@ int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, cons
     const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
     const size_t rho_b = (size_t)batch * D * D * sizeof(double2);
     CU(h->in_dev.reserve(in_elems * sizeof(double2)));
-    CU(h->out_dev.reserve(std::max<size_t>(out_b, 8)));
+    double *d_out = out_b ? mapped_alias(W_out) : nullptr;
+    const bool direct = d_out != nullptr;
+    if (!direct) {
+        CU(h->out_dev.reserve(std::max<size_t>(out_b, 8)));
+        d_out = (double *)h->out_dev.ptr;
+    }
     CU(h->rho_dev.reserve(rho_b));
     HostTimer timer(h);
     CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, batch, psi_stride, dx, nx,
-                              dy, ny, g, (double *)h->out_dev.ptr, (double2 *)h->rho_dev.ptr, h->stream);
+                              dy, ny, g, d_out, (double2 *)h->rho_dev.ptr, h->stream);
     if (rc) return rc;
     if (rho_out) CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, rho_b, cudaMemcpyDeviceToHost, h->stream));
-    if (out_b) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    if (out_b && !direct) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
     return timer.finish();
 }
 

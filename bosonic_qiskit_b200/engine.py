@@ -58,6 +58,8 @@ def _n_qubits(dim: int) -> int:
 class Engine:
     """Owns a ``bq_handle_t`` on one CUDA device."""
 
+    PINNED_POOL_LIMIT = 2 << 30  # bytes of recycled pinned host buffers kept per engine
+
     def __init__(self, device: int = 0):
         self._lib = _lib.load()
         h = ctypes.c_void_p()
@@ -65,6 +67,9 @@ class Engine:
         self._h = h
         self.device = int(device)
         self._finalizer = weakref.finalize(self, self._lib.bq_destroy, h)
+        self._pool: dict[int, list[int]] = {}
+        self._pool_bytes = 0
+        self._pool_lock = threading.Lock()
 
     def close(self) -> None:
         self._finalizer()
@@ -100,15 +105,42 @@ class Engine:
         return float(ms.value), int(n.value)
 
     def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
-        """NumPy array in page-locked host memory (freed when the array is collected)."""
+        """NumPy array in page-locked, device-mapped host memory.
+
+        Outputs placed here are written by the GPU directly (no staging copy).  Buffers come from a
+        small per-engine pool and return to it when the array is garbage collected, because pinning
+        pages costs far more than the kernels this library runs.
+        """
         dtype = np.dtype(dtype)
-        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
-        p = ctypes.c_void_p()
-        check(self._lib.bq_host_alloc(self._h, nbytes, ctypes.byref(p)))
-        buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
-        arr = np.frombuffer(buf, dtype=dtype, count=nbytes // dtype.itemsize).reshape(shape)
-        weakref.finalize(buf, self._lib.bq_host_free, self._h, p)
+        count = int(np.prod(shape, dtype=np.int64))
+        nbytes = count * dtype.itemsize
+        cap = max(65536, -(-nbytes // 65536) * 65536)
+        ptr = None
+        with self._pool_lock:
+            free = self._pool.get(cap)
+            if free:
+                ptr = free.pop()
+                self._pool_bytes -= cap
+        if ptr is None:
+            p = ctypes.c_void_p()
+            check(self._lib.bq_host_alloc(self._h, cap, ctypes.byref(p)))
+            ptr = int(p.value)
+        buf = (ctypes.c_char * cap).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        weakref.finalize(buf, Engine._recycle, weakref.ref(self), cap, ptr)
         return arr
+
+    @staticmethod
+    def _recycle(self_ref, cap: int, ptr: int) -> None:
+        self = self_ref()
+        if self is None or not self._finalizer.alive:
+            return  # engine gone: bq_destroy does not own these, the process is exiting
+        with self._pool_lock:
+            if self._pool_bytes + cap <= self.PINNED_POOL_LIMIT:
+                self._pool.setdefault(cap, []).append(ptr)
+                self._pool_bytes += cap
+                return
+        self._lib.bq_host_free(self._h, ctypes.c_void_p(ptr))
 
     # ------------------------------------------------------------------ partial trace (host)
     def partial_trace_sv(self, psi, traced: Sequence[int]) -> np.ndarray:
@@ -183,7 +215,7 @@ class Engine:
         yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
         shape = (batch, len(yvec), len(xvec))
         if out is None:
-            out = np.empty(shape, dtype=np.float64)
+            out = self.pinned_empty(shape, np.float64)  # the kernel writes host memory directly
         elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out has the wrong shape / dtype / layout")
         check(self._lib.bq_wigner_host(self._h, _ptr(rho3), N, N, N * N, batch, _ptr(xvec), len(xvec), _ptr(yvec),
@@ -204,7 +236,7 @@ class Engine:
         yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
         shape = (batch, len(yvec), len(xvec))
         if out is None:
-            out = np.empty(shape, dtype=np.float64)
+            out = self.pinned_empty(shape, np.float64)  # the kernel writes host memory directly
         elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
             raise ValueError("out has the wrong shape / dtype / layout")
         D = 1 << max(n - len(traced), 0)
