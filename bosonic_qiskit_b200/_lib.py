@@ -48,6 +48,7 @@ SIGNATURES = {
     "bq_fp64_peak": (c_int, [_H, c_double, _dp]),
     "bq_last_device_ms": (c_int, [_H, _dp]),
     "bq_profile_enable": (c_int, [_H, c_int]),
+    "bq_set_sass_mode": (c_int, [_H, c_int, _ip]),
     "bq_profile_read": (c_int, [_H, _dp, _ip]),
     "bq_device_alloc": (c_int, [_H, c_size_t, POINTER(c_void_p)]),
     "bq_device_free": (c_int, [_H, c_void_p]),

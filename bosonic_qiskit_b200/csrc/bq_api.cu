@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -387,6 +388,10 @@ int bq_create(bq_handle_t *out, int device)
     h->dev.device = device;
     h->dev.sm_count = prop.multiProcessorCount;
     h->dev.smem_optin = prop.sharedMemPerBlockOptin;
+    {
+        const char *env = std::getenv("BQ_B200_SASS");
+        h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
+    }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&h->ev_t0) == cudaSuccess && cudaEventCreate(&h->ev_t1) == cudaSuccess &&
@@ -817,6 +822,17 @@ int bq_last_device_ms(bq_handle_t h, double *ms)
 {
     if (!h || !ms) return fail(BQ_ERR_INVALID, "NULL argument");
     *ms = h->last_ms;
+    return BQ_OK;
+}
+
+int bq_set_sass_mode(bq_handle_t h, int mode, int *active)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (mode != 0 && mode != 1) return fail(BQ_ERR_INVALID, "sass mode must be 0 or 1");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    h->dev.sass_mode = (mode == 1 && bq::patched_sass_available()) ? 1 : 0;
+    if (active) *active = h->dev.sass_mode;
     return BQ_OK;
 }
 

@@ -20,6 +20,7 @@ struct DeviceInfo {
     int sm_count = 0;
     size_t smem_optin = 0;
     // per-kernel launch cache (attribute set once, occupancy looked up once per shared-memory size)
+    int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     bool configured[kKernelSlots] = {};
     int occ[kKernelSlots] = {};
     size_t occ_smem[kKernelSlots] = {};
@@ -48,6 +49,7 @@ cudaError_t launch_build_tab(double4 *tab, int N, cudaStream_t st);
 cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, int N, int batch, double2 *cs,
                             int64_t cs_stride, cudaStream_t st);
 cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches);
+bool patched_sass_available();
 
 // K1: rho[set][b] = Psi Psi^dagger.  `maps` is a device array of n_sets TraceMaps (same n_keep / n_trace);
 // rho_out is [n_sets][batch][D][D]; `partial` is scratch of at least trace_sv_scratch_bytes().

@@ -391,23 +391,74 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Re-scheduled SASS.  The build compiles this file to a cubin, runs bosonic_qiskit_b200/_sass_resched.py
+// over it (same instructions, DFMAs re-ordered into operand-reuse chains, see that file) and embeds the
+// result; at run time the embedded image is loaded with cudaLibraryLoadData and its kernels are launched
+// instead of the nvcc-scheduled ones.  sass_mode 0 (or a build without the image) uses the plain kernels.
+// ------------------------------------------------------------------------------------------------
+#ifdef BQ_PATCHED_CUBIN
+#include "wigner_cubin.inc"  // static const unsigned char kWignerCubin[]; generated by _build.py
+#endif
+
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
+constexpr int kVariants = 5;
 
-template <typename Kern>
-cudaError_t run(Kern kern, int slot, int threads, size_t smem, WigParams &p, int pts, DeviceInfo &dev,
+const char *const kKernelNames[kVariants] = {
+    "_ZN2bq22wigner_resident_kernelILi4ELi256ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_resident_kernelILi2ELi128ELi4EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_resident_kernelILi1ELi128ELi4EEEvNS_9WigParamsE",
+    "_ZN2bq20wigner_stream_kernelILi4ELi256ELi4ELi256EEEvNS_9WigParamsE",
+    "_ZN2bq20wigner_stream_kernelILi2ELi128ELi4ELi256EEEvNS_9WigParamsE",
+};
+
+struct Patched {
+    bool ok = false;
+    const void *func[kVariants] = {};
+};
+
+const Patched &patched_kernels()
+{
+    static const Patched pk = [] {
+        Patched r;
+#ifdef BQ_PATCHED_CUBIN
+        cudaLibrary_t lib = nullptr;
+        if (cudaLibraryLoadData(&lib, kWignerCubin, nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return r;
+        }
+        for (int v = 0; v < kVariants; ++v) {
+            cudaKernel_t k = nullptr;
+            if (cudaLibraryGetKernel(&k, lib, kKernelNames[v]) != cudaSuccess) {
+                cudaGetLastError();
+                return r;
+            }
+            r.func[v] = (const void *)k;
+        }
+        r.ok = true;
+#endif
+        return r;
+    }();
+    return pk;
+}
+
+cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigParams &p, int pts, DeviceInfo &dev,
                 cudaStream_t st, int *launches)
 {
+    const bool use_patched = dev.sass_mode != 0 && patched_kernels().ok;
+    const void *func = use_patched ? patched_kernels().func[variant] : plain;
+    const int slot = variant + (use_patched ? kVariants : 0);
     cudaError_t e;
     if (!dev.configured[slot]) {
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.smem_optin);
+        e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dev.smem_optin);
         if (e != cudaSuccess) return e;
         dev.configured[slot] = true;
     }
     if (dev.occ[slot] == 0 || dev.occ_smem[slot] != smem) {
         int occ = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, func, threads, smem);
         if (e != cudaSuccess) return e;
         if (occ < 1) return cudaErrorLaunchOutOfResources;
         dev.occ[slot] = occ;
@@ -423,12 +474,15 @@ cudaError_t run(Kern kern, int slot, int threads, size_t smem, WigParams &p, int
     const int resident = dev.occ[slot] * dev.sm_count;
     const int grid = (int)min((int64_t)resident, (int64_t)p.total_tiles);
     p.grab = max(1, p.total_tiles / (grid * 8));
-    kern<<<grid, threads, smem, st>>>(p);
+    void *args[] = {(void *)&p};
+    e = cudaLaunchKernel(func, dim3(grid), dim3(threads), args, smem, st);
     if (launches) ++*launches;
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace
+
+bool patched_sass_available() { return patched_kernels().ok; }
 
 // Chooses the tile shape so that small grids still cover every SM, then launches.
 cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches)
@@ -439,15 +493,15 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
     if (p.N <= kResidentMaxN) {
         const size_t smem = (size_t)p.R_tot * 48 + 64;
         if (points / (256 * 4) >= 2 * want)
-            return run(wigner_resident_kernel<4, 256, 2>, 0, 256, smem, p, 4, dev, st, launches);
+            return run((const void *)wigner_resident_kernel<4, 256, 2>, 0, 256, smem, p, 4, dev, st, launches);
         if (points / (128 * 2) >= 2 * want)
-            return run(wigner_resident_kernel<2, 128, 4>, 1, 128, smem, p, 2, dev, st, launches);
-        return run(wigner_resident_kernel<1, 128, 4>, 2, 128, smem, p, 1, dev, st, launches);
+            return run((const void *)wigner_resident_kernel<2, 128, 4>, 1, 128, smem, p, 2, dev, st, launches);
+        return run((const void *)wigner_resident_kernel<1, 128, 4>, 2, 128, smem, p, 1, dev, st, launches);
     }
     const size_t smem = (size_t)kStages * kChunk * 48 + 2 * kStages * 8 + 64;
     if (points / (256 * 4) >= want)
-        return run(wigner_stream_kernel<4, 256, kStages, kChunk>, 3, 256, smem, p, 4, dev, st, launches);
-    return run(wigner_stream_kernel<2, 128, kStages, kChunk>, 4, 128, smem, p, 2, dev, st, launches);
+        return run((const void *)wigner_stream_kernel<4, 256, kStages, kChunk>, 3, 256, smem, p, 4, dev, st, launches);
+    return run((const void *)wigner_stream_kernel<2, 128, kStages, kChunk>, 4, 128, smem, p, 2, dev, st, launches);
 }
 
 }  // namespace bq

@@ -94,6 +94,13 @@ class Engine:
         check(self._lib.bq_fp64_peak(self._h, float(seconds), ctypes.byref(v)))
         return float(v.value)
 
+    def set_sass_mode(self, patched: bool) -> bool:
+        """Launch the re-scheduled SASS of the Wigner kernels (True) or nvcc's own schedule (False).
+        Returns what is in effect (False when the build carries no patched image)."""
+        active = ctypes.c_int()
+        check(self._lib.bq_set_sass_mode(self._h, 1 if patched else 0, ctypes.byref(active)))
+        return bool(active.value)
+
     def profile(self, on: bool) -> None:
         """Bracket every Wigner-kernel launch with CUDA events (bench.py's roofline leg)."""
         check(self._lib.bq_profile_enable(self._h, 1 if on else 0))

@@ -139,6 +139,11 @@ int bq_last_device_ms(bq_handle_t h, double *ms);
  * stream it is launched on; bq_profile_read synchronises those streams, returns the summed device
  * time and the number of launches since the last read, and clears the record.                    */
 int bq_profile_enable(bq_handle_t h, int on);
+/* Which machine code of the Wigner kernels is launched: mode 1 = the build's re-scheduled SASS (same
+ * instructions as nvcc's output, DFMAs re-ordered into operand-reuse chains; the default when the build
+ * carries it, overridable with the environment variable BQ_B200_SASS=plain), mode 0 = exactly what nvcc
+ * scheduled.  Results are bit-identical.  *active (may be NULL) receives the mode in effect.            */
+int bq_set_sass_mode(bq_handle_t h, int mode, int *active);
 int bq_profile_read(bq_handle_t h, double *total_ms, int *launches);
 
 /* ---- CUDA IPC plumbing for the multi-GPU tile gather ---------------------------------------- */

@@ -24,11 +24,13 @@ def main():
     ap.add_argument("--grid", type=int, default=2048)
     ap.add_argument("--cutoffs", default="16,32,64,128,256,512,1024")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--sass", default="patched", choices=["patched", "plain"])
     args = ap.parse_args()
     eng = get_engine(0)
     dev = torch.device("cuda", 0)
+    active = eng.set_sass_mode(args.sass == "patched")
     peak = eng.fp64_peak_tflops(1.0)
-    print(json.dumps({"fp64_peak_tflops_measured": peak}), flush=True)
+    print(json.dumps({"fp64_peak_tflops_measured": peak, "sass": "patched" if active else "plain"}), flush=True)
     for N in [int(c) for c in args.cutoffs.split(",")]:
         S = args.grid if N <= 256 else max(512, args.grid // (2 if N == 512 else 4))
         rho = torch.from_numpy(workloads.random_rho(N, seed=N, rank=min(N, 8))).to(dev)
