@@ -296,12 +296,35 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
             raise Giveup(f"control flow inside the loop: {x.text}")
         if x.kind == "fixed" and UNSUPPORTED.match(x.text):
             raise Giveup(f"unsupported instruction in loop: {x.text}")
-    for x in body:
+    # Instructions that stay in place (integer address arithmetic, predicates, the branch) and the address
+    # registers of the loads: every register they mention, taken two registers wide, with the span of body
+    # positions over which they mention it and whether the first mention is a plain definition.
+    fixed_span, fixed_first_is_def = {}, {}
+    for k, x in enumerate(body):
         if x.kind in ("fixed", "bra"):
-            fixed_regs.update(int(m) for m in VREG.findall(x.text))
-        elif x.kind == "lds":  # address registers of the loads stay what they are
+            op = _opcode(x.text)[0]
+            narrow = (op.startswith(("IMAD", "IADD3", "VIADD", "ISETP", "LOP3", "SHF", "LEA", "MOV", "SEL", "IMNMX", "VIMNMX",
+                                     "BRA", "NOP", "UIADD3", "UISETP", "ULEA", "UMOV", "ULOP3", "USEL", "UIMAD"))
+                      and ".WIDE" not in op and ".64" not in op)
+            wd = (0,) if narrow else (0, 1)
+            toks = [int(m) for m in VREG.findall(x.text)]
+            mentioned = {r + d for r in toks for d in wd}
+            first = re.match(r"(@!?U?P\d+\s+)?\S+\s+R(\d+)\s*,", x.text)
+            dreg = int(first.group(2)) if first and not x.text.startswith("@") else None
+            # a plain definition: the destination register does not also appear among the sources
+            is_def = {r: (dreg is not None and r - dreg in wd and toks.count(dreg) == 1 and r - dreg >= 0) for r in mentioned}
+        elif x.kind == "lds":
             am = re.search(r"\[(.*)\]", x.text)
-            fixed_regs.update(int(m) for m in VREG.findall(am.group(1) if am else ""))
+            mentioned = {int(m) for m in VREG.findall(am.group(1) if am else "")}
+            is_def = {r: False for r in mentioned}
+        else:
+            continue
+        for r in mentioned:
+            fixed_regs.add(r)
+            if r not in fixed_span:
+                fixed_span[r] = [k, k]
+                fixed_first_is_def[r] = is_def[r]
+            fixed_span[r][1] = k
     dslots = [k for k, x in enumerate(body) if x.kind == "dfma"]
     nd = len(dslots)
     dfma_index = {k: j for j, k in enumerate(dslots)}
@@ -324,8 +347,15 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
         for r in x.dst:
             last_writer[r] = k
     written = set(last_writer)
-    if {r + d for r in fixed_regs for d in range(4)} & written:
-        raise Giveup("an instruction that stays in place touches a register the loop's FP64 code writes")
+    # A register shared between the stationary instructions and the FP64 code is only tolerated as a scratch
+    # register of the former: defined by them before they read it, never an FP64 operand coming into the body.
+    shared = fixed_regs & written
+    for r in shared:
+        if not fixed_first_is_def[r] or r in live_in:
+            raise Giveup(f"R{r} carries a value between the FP64 code and an instruction that stays in place")
+    for k, x in enumerate(body):
+        if x.kind == "dfma" and any(p is None and ({r, r + 1} & shared) for slot, r, p in reads[k]):
+            raise Giveup("an FP64 operand is produced by an instruction that stays in place")
 
     # Registers that are live around the loop must end the body holding what ptxas left in them: the last
     # writer of such a register is pinned to it.
@@ -499,6 +529,8 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
                 last_use[key] = max(last_use.get(key, -1), k_new)
     pool = set(written) | set(extra_regs)
     busy_until = {r: last_use.get(("in", r), -1) for r in written if r in live_in}
+    for r in shared:  # scratch registers of the stationary instructions: theirs until they are done with them
+        busy_until[r] = max(busy_until.get(r, -1), fixed_span[r][1])
     # a pinned final value owns its register from its definition to the end of the body
     reserved_from = {r: new_pos[k] for r, k in final_writer.items() if k is not None}
     assign = {}
@@ -627,8 +659,10 @@ def model_cycles(words, body, prog):
 
 
 # ------------------------------------------------------------------------------------------------
-def patch_file(src, dst, min_dfma=24, verbose=False, max_regs=None, only=None):
-    """Patches every innermost loop with at least `min_dfma` DFMAs; returns the report lines."""
+def patch_file(src, dst, min_dfma=24, verbose=False, max_regs=None, only=None, max_regs_for=()):
+    """Patches every innermost loop with at least `min_dfma` DFMAs; returns the report lines.
+    max_regs: register budget per thread the loops may grow into (None: only the registers ptxas used);
+    max_regs_for: [(kernel-name regex, budget)] overrides, first match wins."""
     data = bytearray(open(src, "rb").read())
     secs = {s["name"]: s for s in elf_sections(bytes(data))}
     regrec = regcount_records(bytes(data), secs)
@@ -638,6 +672,7 @@ def patch_file(src, dst, min_dfma=24, verbose=False, max_regs=None, only=None):
         if sec is None or (only and not re.search(only, name)):
             continue
         sym = sec["info"]
+        limit = next((v for rx, v in max_regs_for if re.search(rx, name)), max_regs)
         loops = find_loops(ins)
         for lo, hi in loops:
             body = ins[lo:hi + 1]
@@ -650,10 +685,10 @@ def patch_file(src, dst, min_dfma=24, verbose=False, max_regs=None, only=None):
             # registers no instruction of the kernel names, up to the launch-bound limit (the top two registers of
             # an allocation are not addressable): free for the loop's temporaries
             extra = ()
-            if max_regs and sym in regrec:
+            if limit and sym in regrec:
                 top = max((int(m) for x in ins for m in VREG.findall(x.text)), default=0)
                 first = max(regrec[sym][1] - 2, top + 4)
-                extra = tuple(range(first + first % 2, max_regs - 2))
+                extra = tuple(range(first + first % 2, limit - 2))
             try:
                 words, info = reschedule(body, verbose, live_after=live_registers_at(ins, hi + 1), extra_regs=extra)
             except Giveup as e:
@@ -664,7 +699,7 @@ def patch_file(src, dst, min_dfma=24, verbose=False, max_regs=None, only=None):
                 assert int.from_bytes(data[off:off + 16], "little") == x.word, "disassembly / section offset mismatch"
                 data[off:off + 16] = w.to_bytes(16, "little")
             if sym in regrec and info["used_max"] + 3 > regrec[sym][1]:
-                newcount = min(max_regs, -(-(info["used_max"] + 3) // 8) * 8)
+                newcount = min(limit, -(-(info["used_max"] + 3) // 8) * 8)
                 struct.pack_into("<I", data, regrec[sym][0], newcount)
                 report.append(f"{tag}: register count {regrec[sym][1]} -> {newcount}")
                 regrec[sym] = (regrec[sym][0], newcount)

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_resident_kernel(const Wi
 // N > 64: coefficient stream pulled through a shared-memory ring by bulk copies
 // ------------------------------------------------------------------------------------------------
 template <int PTS, int THREADS, int STAGES, int CHUNK>
-__global__ void __launch_bounds__(THREADS, 2) wigner_stream_kernel(const WigParams p)
+__global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigParams p)
 {
     constexpr int NWARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -327,7 +327,10 @@ __global__ void __launch_bounds__(THREADS, 2) wigner_stream_kernel(const WigPara
         for (int k = 0; k < PTS; ++k) s.y0r[k] = s.y0i[k] = s.y1r[k] = s.y1i[k] = 0.0;
 
         for (int ci = 0; ci < n_chunks; ++ci) {
-            const uint32_t G = gc + ci, st = G % STAGES, use = G / STAGES;
+            // gc is the same in every thread, but it depends on how many tiles this CTA happened to grab, which
+            // the compiler cannot see; the lane-0 broadcast tells it the ring position is warp-uniform, so the
+            // shared-memory addresses of the hot loop live in uniform registers (as in the resident kernel).
+            const uint32_t G = __shfl_sync(0xffffffffu, gc + (uint32_t)ci, 0), st = G % STAGES, use = G / STAGES;
             mbar_wait(&full[st], use & 1u);
             const double2 *cp = cs_s + (size_t)st * CHUNK;
             const double4 *tp = tab_s + (size_t)st * CHUNK;
@@ -344,9 +347,12 @@ __global__ void __launch_bounds__(THREADS, 2) wigner_stream_kernel(const WigPara
             }
             while (r < nrec) {
                 if (rem > 0) {
-                    const int m = min(rem, nrec - r);
-                    const double2 *c = cp + r;
-                    const double4 *t = tp + r;
+                    // (lane-0 broadcasts: r and rem are the same in every thread; saying so keeps the loop counter
+                    // and the shared-memory addresses of the hot loop in uniform registers)
+                    const int m = __shfl_sync(0xffffffffu, min(rem, nrec - r), 0);
+                    const int r0 = __shfl_sync(0xffffffffu, r, 0);
+                    const double2 *c = cp + r0;
+                    const double4 *t = tp + r0;
                     int i = 0;
                     for (; i + 1 < m; i += 2) {
                         clenshaw_step<PTS>(s, c[i], t[i]);
