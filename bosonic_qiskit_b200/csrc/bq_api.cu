@@ -389,6 +389,8 @@ int bq_create(bq_handle_t *out, int device)
     h->dev.sm_count = prop.multiProcessorCount;
     h->dev.smem_optin = prop.sharedMemPerBlockOptin;
     {
+        const char *p8 = std::getenv("BQ_B200_PTS8");
+        h->dev.pts8 = (p8 && p8[0] == '0') ? 0 : 1;  // default on: measured 87.6 % vs 82.7 % of fp64 peak at N=64
         const char *env = std::getenv("BQ_B200_SASS");
         h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
     }

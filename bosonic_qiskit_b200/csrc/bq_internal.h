@@ -20,6 +20,7 @@ struct DeviceInfo {
     int sm_count = 0;
     size_t smem_optin = 0;
     // per-kernel launch cache (attribute set once, occupancy looked up once per shared-memory size)
+    int pts8 = 0;       // use the 8-points-per-thread resident kernel for large grids
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     bool configured[kKernelSlots] = {};
     int occ[kKernelSlots] = {};

@@ -260,12 +260,14 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_resident_kernel(const Wi
             const double4 *tp = tab_s + pos + 2;
             const int m = K - 2;
             int r = 0;
+            // (Software-pipelining these loads through explicit register buffers was tried and measured slower:
+            // 82.8 % vs 87.6 % of the fp64 peak at N=64 -- the loads are not what the warps wait for.)
             for (; r + 1 < m; r += 2) {
                 clenshaw_step<PTS>(s, cp[r], tp[r]);
                 clenshaw_step<PTS>(s, cp[r + 1], tp[r + 1]);
             }
             if (r < m) clenshaw_step<PTS>(s, cp[r], tp[r]);
-            horner_tail<PTS>(s, tab_s[pos + K]);
+            horner_tail<PTS>(s, tp[m]);
             pos += K + 1;
         }
         store_points<PTS>(p, frame, iy, ix0, s);
@@ -410,7 +412,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 5;
+constexpr int kVariants = 6;
 
 const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_resident_kernelILi4ELi256ELi2EEEvNS_9WigParamsE",
@@ -418,6 +420,7 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_resident_kernelILi1ELi128ELi4EEEvNS_9WigParamsE",
     "_ZN2bq20wigner_stream_kernelILi4ELi256ELi4ELi256EEEvNS_9WigParamsE",
     "_ZN2bq20wigner_stream_kernelILi2ELi128ELi4ELi256EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_resident_kernelILi8ELi128ELi2EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -498,8 +501,11 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
     const int64_t want = 2LL * dev.sm_count;  // tiles needed before the big tile pays off
     if (p.N <= kResidentMaxN) {
         const size_t smem = (size_t)p.R_tot * 48 + 64;
-        if (points / (256 * 4) >= 2 * want)
+        if (points / (256 * 4) >= 2 * want) {
+            // 8 points per thread halve the shared-memory loads per DFMA (same 1024-point tile, 128 threads)
+            if (dev.pts8) return run((const void *)wigner_resident_kernel<8, 128, 2>, 5, 128, smem, p, 8, dev, st, launches);
             return run((const void *)wigner_resident_kernel<4, 256, 2>, 0, 256, smem, p, 4, dev, st, launches);
+        }
         if (points / (128 * 2) >= 2 * want)
             return run((const void *)wigner_resident_kernel<2, 128, 4>, 1, 128, smem, p, 2, dev, st, launches);
         return run((const void *)wigner_resident_kernel<1, 128, 4>, 2, 128, smem, p, 1, dev, st, launches);
