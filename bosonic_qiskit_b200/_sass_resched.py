@@ -299,7 +299,7 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
     # Instructions that stay in place (integer address arithmetic, predicates, the branch) and the address
     # registers of the loads: every register they mention, taken two registers wide, with the span of body
     # positions over which they mention it and whether the first mention is a plain definition.
-    fixed_span, fixed_first_is_def = {}, {}
+    fixed_span, fixed_first_is_def, fixed_ranges = {}, {}, {}
     for k, x in enumerate(body):
         if x.kind in ("fixed", "bra"):
             op = _opcode(x.text)[0]
@@ -325,6 +325,12 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
                 fixed_span[r] = [k, k]
                 fixed_first_is_def[r] = is_def[r]
             fixed_span[r][1] = k
+            # def-use ranges of the stationary instructions' own values: a plain definition opens a range,
+            # every later mention extends it
+            if is_def[r] or r not in fixed_ranges:
+                fixed_ranges.setdefault(r, []).append([k, k])
+            else:
+                fixed_ranges[r][-1][1] = k
     dslots = [k for k, x in enumerate(body) if x.kind == "dfma"]
     nd = len(dslots)
     dfma_index = {k: j for j, k in enumerate(dslots)}
@@ -362,6 +368,9 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
     keep = {r for r in written if r in live_in or r in live_after}
     keep |= {r ^ 1 for r in keep}  # 64-bit values are pinned as a whole
     keep &= written
+    # a register a stationary instruction redefines after the FP64 code's last write to it ends the body holding
+    # that instruction's value, not an FP64 one
+    keep -= {r for r in shared if fixed_ranges[r][-1][0] > last_writer[r]}
     final_writer = {r: (k if r in keep else None) for r, k in last_writer.items()}
     pinned = {k for k, x in enumerate(body) if x.dst and any(final_writer[r] == k for r in x.dst)}
 
@@ -410,6 +419,22 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
                         before[dfma_index[k]].add(dfma_index[rd])
                     else:
                         lds_after[dfma_index[rd]] = min(lds_after.get(dfma_index[rd], n), k)
+    # a pinned FP64 value in a register that stationary instructions also use as scratch: it must be defined after
+    # their earlier ranges and fully read before their later ones
+    not_before = {}  # DFMA j may only sit in a slot after this body position
+    for k in pinned:
+        x = body[k]
+        for off, r in enumerate(x.dst):
+            for a, b in fixed_ranges.get(r, ()) if r in shared else ():
+                if a < k:
+                    if x.kind != "dfma":
+                        if b >= k:
+                            raise Giveup(f"R{r}: a load that must stay in R{r} overlaps a stationary instruction's use of it")
+                        continue
+                    not_before[dfma_index[k]] = max(not_before.get(dfma_index[k], -1), b)
+                else:
+                    for rd in readers.get((k, off - off % 2), ()):
+                        lds_after[dfma_index[rd]] = min(lds_after.get(dfma_index[rd], n), a)
 
     # ---- deadlines (as-late-as-possible slot) so the greedy pass cannot paint itself into a corner ----------
     deadline = [nd - 1] * nd
@@ -464,7 +489,7 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
         def wait_needed(j):
             if any(i in remaining for i in dpreds[j] | before[j]):
                 return None  # not schedulable yet
-            if any(p > k for p in lpreds[j]) or lds_after.get(j, n) < k:
+            if any(p > k for p in lpreds[j]) or lds_after.get(j, n) < k or k <= not_before.get(j, -1):
                 return None
             need = max([issue[i] + DFMA_LAT for i in dpreds[j]], default=0)
             return max(0, need - clock)
@@ -529,8 +554,11 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
                 last_use[key] = max(last_use.get(key, -1), k_new)
     pool = set(written) | set(extra_regs)
     busy_until = {r: last_use.get(("in", r), -1) for r in written if r in live_in}
-    for r in shared:  # scratch registers of the stationary instructions: theirs until they are done with them
-        busy_until[r] = max(busy_until.get(r, -1), fixed_span[r][1])
+
+    def clear_of_stationary(r, lo, hi):
+        """no stationary instruction uses register r as scratch anywhere in body positions [lo, hi]"""
+        return not any(a <= hi and lo <= b for a, b in (fixed_ranges.get(r, ()) if r in shared else ()))
+
     # a pinned final value owns its register from its definition to the end of the body
     reserved_from = {r: new_pos[k] for r, k in final_writer.items() if k is not None}
     assign = {}
@@ -539,12 +567,15 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
         ends = [max(last_use.get((k, off), k_new), k_new) for off in range(x.dst_width)]
         if k in pinned:
             for off, r in enumerate(x.dst):
-                if busy_until.get(r, -1) >= k_new:
+                if busy_until.get(r, -1) > k_new:  # == k_new: this very instruction is the last reader
                     raise Giveup(f"R{r} still holds a needed value where {x.text} must be defined")
+                if not clear_of_stationary(r, k_new, n if final_writer[r] == k else ends[off]):
+                    raise Giveup(f"R{r}: {x.text} would overlap a stationary instruction's use of the register")
                 if final_writer[r] == k:
                     busy_until[r] = n
                 else:
-                    if reserved_from.get(r, n + 1) <= ends[off]:
+                    # (equality: the instruction that redefines the register is itself the last reader)
+                    if reserved_from.get(r, n + 1) < ends[off]:
                         raise Giveup(f"R{r}: part of {x.text} would be overwritten before its last use")
                     busy_until[r] = ends[off]
             assign[k] = x.dst_base
@@ -553,8 +584,8 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
         for base in sorted(pool):
             if base % x.dst_width or any((base + off) not in pool for off in range(x.dst_width)):
                 continue
-            if all(busy_until.get(base + off, -1) < k_new and reserved_from.get(base + off, n + 1) > ends[off]
-                   for off in range(x.dst_width)):
+            if all(busy_until.get(base + off, -1) < k_new and reserved_from.get(base + off, n + 1) >= ends[off]
+                   and clear_of_stationary(base + off, k_new, ends[off]) for off in range(x.dst_width)):
                 choice = base
                 break
         if choice is None:

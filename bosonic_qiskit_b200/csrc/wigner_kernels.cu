@@ -300,7 +300,11 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
     __syncthreads();
 
     const int n_chunks = (p.R_tot + CHUNK - 1) / CHUNK;
-    uint32_t gc = 0;  // chunks this CTA has gone through so far (uniform across the CTA)
+    // Ring position of chunk ci is ci % STAGES in every tile, so every shared-memory address of the hot loop is a
+    // function of loop counters and kernel parameters only (warp-uniform: uniform registers).  What does depend on
+    // how many tiles this CTA has processed -- the phase parity of each mbarrier -- is tracked in two bit masks.
+    uint32_t full_phase = 0;   // bit st: parity the consumers wait for next on full[st]
+    uint32_t fill_count = 0;   // bit st: parity of the number of times stage st has been filled (producer thread)
     TileCursor tc{0, 0};
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
@@ -308,9 +312,10 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
         const int tif = tile - frame * p.tiles_per_frame;
         const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
 
-        auto produce = [&](uint32_t G, int ci) {
-            const uint32_t st = G % STAGES, use = G / STAGES;
-            mbar_wait(&empty[st], (use & 1u) ^ 1u);
+        auto produce = [&](int ci) {
+            const uint32_t st = (uint32_t)ci % STAGES;
+            mbar_wait(&empty[st], ((fill_count >> st) & 1u) ^ 1u);  // previous contents consumed by every warp
+            fill_count ^= 1u << st;
             const int recs = min(CHUNK, p.R_tot - ci * CHUNK);
             mbar_arrive_expect_tx(&full[st], (uint32_t)recs * 48u);
             bulk_g2s(tab_s + (size_t)st * CHUNK, p.tab + (int64_t)ci * CHUNK, (uint32_t)recs * 32u, &full[st]);
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
         };
         if (tid == 0) {
             const int pre = min(STAGES - 1, n_chunks);
-            for (int d = 0; d < pre; ++d) produce(gc + d, d);
+            for (int d = 0; d < pre; ++d) produce(d);
         }
 
         Points<PTS> s;
@@ -329,11 +334,9 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
         for (int k = 0; k < PTS; ++k) s.y0r[k] = s.y0i[k] = s.y1r[k] = s.y1i[k] = 0.0;
 
         for (int ci = 0; ci < n_chunks; ++ci) {
-            // gc is the same in every thread, but it depends on how many tiles this CTA happened to grab, which
-            // the compiler cannot see; the lane-0 broadcast tells it the ring position is warp-uniform, so the
-            // shared-memory addresses of the hot loop live in uniform registers (as in the resident kernel).
-            const uint32_t G = __shfl_sync(0xffffffffu, gc + (uint32_t)ci, 0), st = G % STAGES, use = G / STAGES;
-            mbar_wait(&full[st], use & 1u);
+            const uint32_t st = (uint32_t)ci % STAGES;
+            mbar_wait(&full[st], (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
             const double2 *cp = cs_s + (size_t)st * CHUNK;
             const double4 *tp = tab_s + (size_t)st * CHUNK;
             const int nrec = min(CHUNK, p.R_tot - ci * CHUNK);
@@ -349,12 +352,9 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
             }
             while (r < nrec) {
                 if (rem > 0) {
-                    // (lane-0 broadcasts: r and rem are the same in every thread; saying so keeps the loop counter
-                    // and the shared-memory addresses of the hot loop in uniform registers)
-                    const int m = __shfl_sync(0xffffffffu, min(rem, nrec - r), 0);
-                    const int r0 = __shfl_sync(0xffffffffu, r, 0);
-                    const double2 *c = cp + r0;
-                    const double4 *t = tp + r0;
+                    const int m = min(rem, nrec - r);
+                    const double2 *c = cp + r;
+                    const double4 *t = tp + r;
                     int i = 0;
                     for (; i + 1 < m; i += 2) {
                         clenshaw_step<PTS>(s, c[i], t[i]);
@@ -374,9 +374,8 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[st]);
-            if (tid == 0 && ci + STAGES - 1 < n_chunks) produce(G + STAGES - 1, ci + STAGES - 1);
+            if (tid == 0 && ci + STAGES - 1 < n_chunks) produce(ci + STAGES - 1);
         }
-        gc += (uint32_t)n_chunks;
         store_points<PTS>(p, frame, iy, ix0, s);
     }
     leave_grid(p);
@@ -412,7 +411,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 6;
+constexpr int kVariants = 7;
 
 const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_resident_kernelILi4ELi256ELi2EEEvNS_9WigParamsE",
@@ -421,6 +420,7 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq20wigner_stream_kernelILi4ELi256ELi4ELi256EEEvNS_9WigParamsE",
     "_ZN2bq20wigner_stream_kernelILi2ELi128ELi4ELi256EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_resident_kernelILi8ELi128ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq20wigner_stream_kernelILi8ELi128ELi4ELi256EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -512,7 +512,11 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
     }
     const size_t smem = (size_t)kStages * kChunk * 48 + 2 * kStages * 8 + 64;
     if (points / (256 * 4) >= want)
+    {
+        if (dev.pts8)
+            return run((const void *)wigner_stream_kernel<8, 128, kStages, kChunk>, 6, 128, smem, p, 8, dev, st, launches);
         return run((const void *)wigner_stream_kernel<4, 256, kStages, kChunk>, 3, 256, smem, p, 4, dev, st, launches);
+    }
     return run((const void *)wigner_stream_kernel<2, 128, kStages, kChunk>, 4, 128, smem, p, 2, dev, st, launches);
 }
 
