@@ -185,7 +185,10 @@ def _defs_uses(x):
         wd = 4 if ".128" in op else 2 if (".64" in op or op.startswith(("DFMA", "DMUL", "DADD")) or ".WIDE" in op) else 1
         dst = list(range(d, d + wd))
     uses = set()
-    wide = 4 if ".128" in op else 2
+    narrow = (op.startswith(("IMAD", "IADD3", "VIADD", "ISETP", "LOP3", "SHF", "LEA", "MOV", "SEL", "IMNMX", "VIMNMX", "LDS",
+                             "S2R", "CS2R", "PRMT", "I2F", "F2I", "POPC", "FLO", "BREV", "SHFL", "VOTE", "PLOP3"))
+              and ".WIDE" not in op and ".64" not in op)  # 32-bit integer operands; LDS: 32-bit addresses
+    wide = 1 if (narrow or op.startswith("LDS")) else 2 if op.startswith(("LDG", "LD.")) else 4 if ".128" in op else 2
     for a_i, rl in enumerate(regs):
         if a_i == 0 and dst:
             continue
@@ -553,50 +556,55 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=()):
                 key = ("in", r + d) if p is None else (p, r - body[p].dst_base + d)
                 last_use[key] = max(last_use.get(key, -1), k_new)
     pool = set(written) | set(extra_regs)
-    busy_until = {r: last_use.get(("in", r), -1) for r in written if r in live_in}
+    # Interval allocation on a doubled time line: the reads of the instruction at body position k happen at 2k,
+    # its write at 2k+1 (so an instruction may overwrite an operand it reads itself).
+    occupied = {}  # register -> [(start, end)] closed intervals
 
-    def clear_of_stationary(r, lo, hi):
-        """no stationary instruction uses register r as scratch anywhere in body positions [lo, hi]"""
-        return not any(a <= hi and lo <= b for a, b in (fixed_ranges.get(r, ()) if r in shared else ()))
+    def fits(r, a, b):
+        return all(b < lo or hi < a for lo, hi in occupied.get(r, ()))
 
-    # a pinned final value owns its register from its definition to the end of the body
-    reserved_from = {r: new_pos[k] for r, k in final_writer.items() if k is not None}
+    def take(r, a, b):
+        occupied.setdefault(r, []).append((a, b))
+
+    for r in written:
+        if r in live_in:
+            take(r, -1, 2 * last_use.get(("in", r), -1))
+    for r in shared:  # scratch ranges of the stationary instructions
+        for a, b in fixed_ranges[r]:
+            take(r, 2 * a, 2 * b + 1)
+
+    def span(k, off):
+        """interval during which 32-bit part `off` of the value defined by instruction k must stay intact"""
+        d = 2 * new_pos[k] + 1
+        if final_writer[body[k].dst[off]] == k and k in pinned:
+            return d, 2 * n + 1
+        return d, max(2 * last_use.get((k, off), -1), d)
+
     assign = {}
-    for k_new, k in sorted((new_pos[k], k) for k, x in enumerate(body) if x.dst):
+    for k in sorted(pinned, key=lambda k: new_pos[k]):  # pinned values sit where ptxas put them
         x = body[k]
-        ends = [max(last_use.get((k, off), k_new), k_new) for off in range(x.dst_width)]
-        if k in pinned:
-            for off, r in enumerate(x.dst):
-                if busy_until.get(r, -1) > k_new:  # == k_new: this very instruction is the last reader
-                    raise Giveup(f"R{r} still holds a needed value where {x.text} must be defined")
-                if not clear_of_stationary(r, k_new, n if final_writer[r] == k else ends[off]):
-                    raise Giveup(f"R{r}: {x.text} would overlap a stationary instruction's use of the register")
-                if final_writer[r] == k:
-                    busy_until[r] = n
-                else:
-                    # (equality: the instruction that redefines the register is itself the last reader)
-                    if reserved_from.get(r, n + 1) < ends[off]:
-                        raise Giveup(f"R{r}: part of {x.text} would be overwritten before its last use")
-                    busy_until[r] = ends[off]
-            assign[k] = x.dst_base
-            continue
+        for off, r in enumerate(x.dst):
+            a, b = span(k, off)
+            if not fits(r, a, b):
+                raise Giveup(f"R{r} is not free for {x.text}, which must stay in it")
+            take(r, a, b)
+        assign[k] = x.dst_base
+    # then the widest values first (aligned quads fragment the file least when placed early), each by position
+    free_values = [k for k, x in enumerate(body) if x.dst and k not in pinned]
+    for k in sorted(free_values, key=lambda k: (-body[k].dst_width, new_pos[k])):
+        x = body[k]
+        spans = [span(k, off) for off in range(x.dst_width)]
         choice = None
         for base in sorted(pool):
             if base % x.dst_width or any((base + off) not in pool for off in range(x.dst_width)):
                 continue
-            if all(busy_until.get(base + off, -1) < k_new and reserved_from.get(base + off, n + 1) >= ends[off]
-                   and clear_of_stationary(base + off, k_new, ends[off]) for off in range(x.dst_width)):
+            if all(fits(base + off, *spans[off]) for off in range(x.dst_width)):
                 choice = base
                 break
         if choice is None:
-            if verbose:
-                print(f"   allocation failure at {k_new} for {x.text}, needs until {ends}")
-                for r in sorted(pool):
-                    print(f"     R{r}: live_in={r in live_in} busy_until={busy_until.get(r, -1)} "
-                          f"reserved_from={reserved_from.get(r, n + 1)}")
-            raise Giveup(f"out of registers for {x.text} at position {k_new}")
+            raise Giveup(f"out of registers for {x.text} at position {new_pos[k]}")
         for off in range(x.dst_width):
-            busy_until[choice + off] = ends[off]
+            take(choice + off, *spans[off])
         assign[k] = choice
 
     def new_reg(r, producer):

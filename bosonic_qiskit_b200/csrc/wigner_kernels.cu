@@ -276,6 +276,127 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_resident_kernel(const Wi
 }
 
 // ------------------------------------------------------------------------------------------------
+// 64 < N <= ~1600: the stream is pulled through a ring of STAGES buffers, each holding WHOLE diagonals
+// (capacity N+1 records = the longest diagonal plus its tail record; short diagonals are packed together).
+// Inside a buffer the code is the resident kernel's: exact initialisation, one clean counted loop per
+// diagonal whose addresses are functions of loop counters only.  Groups are contiguous in the global
+// stream, so a refill is two bulk copies.  One CTA per SM (the ring takes most of the shared memory).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int group_end(int K_first, int first_is_header, int cap, int N)
+{
+    // diagonals K_first .. (returned value - 1) share one buffer
+    int cnt = first_is_header, K = K_first;
+    while (K <= N && cnt + K + 1 <= cap) {
+        cnt += K + 1;
+        ++K;
+    }
+    return K;
+}
+
+template <int PTS, int THREADS, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) wigner_diag_kernel(const WigParams p)
+{
+    constexpr int NWARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = p.N, cap = N + 1;
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)STAGES * cap * 32);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * cap * 48);
+    uint64_t *empty = full + STAGES;
+    int *slot = reinterpret_cast<int *>(empty + STAGES);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t full_phase = 0, fill_count = 0;  // per-stage phase parities (see wigner_stream_kernel)
+    TileCursor tc{0, 0};
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
+
+        // producer cursor (thread 0): next group to load
+        int pg = 0, pK = 2;
+        auto produce = [&]() {
+            const uint32_t st = (uint32_t)pg % STAGES;
+            const int Kend = group_end(pK, pg == 0, cap, N);
+            const int64_t first = (pg == 0) ? 0 : diag_pos(pK);
+            const int64_t last = (Kend <= N) ? diag_pos(Kend) : (int64_t)p.R_tot;
+            const uint32_t recs = (uint32_t)(last - first);
+            mbar_wait(&empty[st], ((fill_count >> st) & 1u) ^ 1u);
+            fill_count ^= 1u << st;
+            mbar_arrive_expect_tx(&full[st], recs * 48u);
+            bulk_g2s(tab_s + (size_t)st * cap, p.tab + first, recs * 32u, &full[st]);
+            bulk_g2s(cs_s + (size_t)st * cap, cs_g + first, recs * 16u, &full[st]);
+            ++pg;
+            pK = Kend;
+        };
+        if (tid == 0)
+            for (int d = 0; d < STAGES - 1 && pK <= N; ++d) produce();
+
+        Points<PTS> s;
+        int iy, ix0;
+        load_points<PTS>(p, tif * THREADS + tid, s, iy, ix0);
+
+        int K = 2;
+        for (int g = 0; K <= N; ++g) {
+            const uint32_t st = (uint32_t)g % STAGES;
+            mbar_wait(&full[st], (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            const double2 *cb = cs_s + (size_t)st * cap;
+            const double4 *tb = tab_s + (size_t)st * cap;
+            int pos = 0;
+            if (g == 0) {
+                const double2 h = cb[0];
+#pragma unroll
+                for (int k = 0; k < PTS; ++k) {
+                    s.wr[k] = h.x;
+                    s.wi[k] = h.y;
+                }
+                pos = 1;
+            }
+            const int Kend = group_end(K, g == 0, cap, N);
+            for (; K < Kend; ++K) {
+                {
+                    const double2 c1 = cb[pos], c0 = cb[pos + 1];
+#pragma unroll
+                    for (int k = 0; k < PTS; ++k) {
+                        s.y1r[k] = c1.x;
+                        s.y1i[k] = c1.y;
+                        s.y0r[k] = c0.x;
+                        s.y0i[k] = c0.y;
+                    }
+                }
+                const double2 *cp = cb + pos + 2;
+                const double4 *tp = tb + pos + 2;
+                const int m = K - 2;
+                int r = 0;
+                for (; r + 1 < m; r += 2) {
+                    clenshaw_step<PTS>(s, cp[r], tp[r]);
+                    clenshaw_step<PTS>(s, cp[r + 1], tp[r + 1]);
+                }
+                if (r < m) clenshaw_step<PTS>(s, cp[r], tp[r]);
+                horner_tail<PTS>(s, tp[m]);
+                pos += K + 1;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+            if (tid == 0 && pK <= N) produce();
+        }
+        store_points<PTS>(p, frame, iy, ix0, s);
+    }
+    leave_grid(p);
+}
+
+// ------------------------------------------------------------------------------------------------
 // N > 64: coefficient stream pulled through a shared-memory ring by bulk copies
 // ------------------------------------------------------------------------------------------------
 template <int PTS, int THREADS, int STAGES, int CHUNK>
@@ -411,7 +532,8 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 7;
+constexpr int kVariants = 8;
+constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_resident_kernelILi4ELi256ELi2EEEvNS_9WigParamsE",
@@ -421,6 +543,7 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq20wigner_stream_kernelILi2ELi128ELi4ELi256EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_resident_kernelILi8ELi128ELi2EEEvNS_9WigParamsE",
     "_ZN2bq20wigner_stream_kernelILi8ELi128ELi4ELi256EEEvNS_9WigParamsE",
+    "_ZN2bq18wigner_diag_kernelILi8ELi256ELi3EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -510,6 +633,10 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             return run((const void *)wigner_resident_kernel<2, 128, 4>, 1, 128, smem, p, 2, dev, st, launches);
         return run((const void *)wigner_resident_kernel<1, 128, 4>, 2, 128, smem, p, 1, dev, st, launches);
     }
+    // whole-diagonal ring: needs 3 x (N+1) records of shared memory and enough points to give every SM a tile
+    const size_t smem_diag = (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
+    if (dev.pts8 && smem_diag <= dev.smem_optin && points / (256 * 8) >= dev.sm_count)
+        return run((const void *)wigner_diag_kernel<8, 256, kDiagStages>, 7, 256, smem_diag, p, 8, dev, st, launches);
     const size_t smem = (size_t)kStages * kChunk * 48 + 2 * kStages * 8 + 64;
     if (points / (256 * 4) >= want)
     {
