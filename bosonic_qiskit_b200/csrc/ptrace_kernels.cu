@@ -24,92 +24,85 @@ __device__ __forceinline__ uint64_t deposit_bits(uint64_t v, const int *pos, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1.  One CTA = one TI x TJ tile of one rho, one split of the traced range.
-// 256 threads = TI*TJ outputs x LT lanes along t.  Operands are staged in shared memory in chunks of
-// TC traced indices; accumulation order over t is fixed (deterministic results).
+// K1.  FP64 tensor-core contraction: one warp = one 8x8 tile of one rho and one split of the traced
+// range, accumulated with mma.sync.aligned.m8n8k4.f64 (DMMA; tcgen05 has no f64 kind, so this is the
+// legacy tensor path on sm_100a).  With Psi = A_r + i A_i,
+//     Re rho = A_r A_r^T + A_i A_i^T,      Im rho = A_i A_r^T - A_r A_i^T :
+// four real MMAs per 4 traced indices.  The "A" fragment (row = lane/4, k = lane%4) and the "col-major B"
+// fragment (k = lane%4, n = lane/4) want the same element Psi[tile row lane/4][t0 + lane%4], so each lane
+// gathers exactly two complex numbers per step straight from global memory (the bit-deposit gather is
+// the operand load) and nothing is staged in shared memory.  Splits of the traced range are reduced in
+// a fixed order by reduce_splits_kernel (deterministic results).
 // ------------------------------------------------------------------------------------------------
-constexpr int kTraceThreads = 256;
-constexpr int kTC = 32;
+constexpr int kTraceWarps = 4;
 
 struct TraceSvParams {
     const double2 *psi;
     int64_t psi_stride;
     const TraceMap *maps;
     double2 *out;  // final rho or partials: [split][set][batch][D][D]
-    int n_keep, n_trace, batch, n_sets, splits;
-    int TI, TJ, LT;
-    int tiles_i, tiles_j;
-    int64_t t_per_split;
+    int n_keep, n_trace, batch, n_sets, splits, tiles;
+    int64_t t_per_split;  // multiple of 4
 };
 
-__global__ void __launch_bounds__(kTraceThreads) trace_sv_kernel(const TraceSvParams p)
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
 {
-    __shared__ double2 As[16][kTC + 1];
-    __shared__ double2 Bs[16][kTC + 1];
-    __shared__ uint64_t row_i[16], row_j[16], toff[kTC];
-    __shared__ double2 red[kTraceThreads];
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(32 * kTraceWarps) trace_sv_dmma_kernel(const TraceSvParams p)
+{
     __shared__ TraceMap map;
-
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int split = blockIdx.y;
-    const int sb = blockIdx.z;  // set * batch + b
+    const int sb = blockIdx.y;  // set * batch + b
     const int set = sb / p.batch, b = sb - set * p.batch;
-    const int ti0 = (tile / p.tiles_j) * p.TI, tj0 = (tile % p.tiles_j) * p.TJ;
-
-    // the map is small: copy it once per CTA
     {
         const int *src = reinterpret_cast<const int *>(p.maps + set);
         int *dst = reinterpret_cast<int *>(&map);
-        for (int i = tid; i < (int)(sizeof(TraceMap) / sizeof(int)); i += kTraceThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(TraceMap) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    if (tid < p.TI) row_i[tid] = deposit_bits((uint64_t)(ti0 + tid), map.keep, p.n_keep);
-    if (tid >= 32 && tid < 32 + p.TJ) row_j[tid - 32] = deposit_bits((uint64_t)(tj0 + tid - 32), map.keep, p.n_keep);
 
+    const int lane = threadIdx.x & 31;
+    const int64_t w = (int64_t)blockIdx.x * kTraceWarps + (threadIdx.x >> 5);
+    const int64_t tiles2 = (int64_t)p.tiles * p.tiles;
+    if (w >= tiles2 * p.splits) return;  // whole warps only
+    const int split = (int)(w / tiles2), tile = (int)(w - (int64_t)split * tiles2);
+    const int I = tile / p.tiles, J = tile - I * p.tiles;
+    const int gi = lane >> 2, kk = lane & 3;
+    const int64_t D = (int64_t)1 << p.n_keep, T = (int64_t)1 << p.n_trace;
+    const int64_t i = (int64_t)I * 8 + gi, j = (int64_t)J * 8 + gi;
+    const bool vi = i < D, vj = j < D;
+    const uint64_t row_i = deposit_bits((uint64_t)(vi ? i : 0), map.keep, p.n_keep);
+    const uint64_t row_j = deposit_bits((uint64_t)(vj ? j : 0), map.keep, p.n_keep);
     const double2 *psi = p.psi + (int64_t)b * p.psi_stride;
-    const int64_t T = (int64_t)1 << p.n_trace;
+
     const int64_t t_begin = (int64_t)split * p.t_per_split;
     const int64_t t_end = min(T, t_begin + p.t_per_split);
+    // traced index of this lane in deposited form; stepping by 4 is a carry-propagating add over the mask
+    uint64_t mask = 0;
+    for (int q = 0; q < p.n_trace; ++q) mask |= 1ull << map.trace[q];
+    const uint64_t step4 = deposit_bits(4ull, map.trace, p.n_trace);
+    uint64_t toff = deposit_bits((uint64_t)(t_begin + kk), map.trace, p.n_trace);
 
-    const int outs = p.TI * p.TJ;
-    const int o = tid % outs, lane_t = tid / outs;  // LT = 256 / outs lanes share one output
-    const int oi = o / p.TJ, oj = o % p.TJ;
-    double accr = 0.0, acci = 0.0;
-
-    for (int64_t t0 = t_begin; t0 < t_end; t0 += kTC) {
-        const int nt = (int)min((int64_t)kTC, t_end - t0);
-        __syncthreads();  // previous chunk consumed (also orders row_i/row_j on the first pass)
-        if (tid < nt) toff[tid] = deposit_bits((uint64_t)(t0 + tid), map.trace, p.n_trace);
-        __syncthreads();
-        for (int e = tid; e < p.TI * kTC; e += kTraceThreads) {
-            const int r = e / kTC, c = e % kTC;
-            As[r][c] = (c < nt) ? psi[row_i[r] | toff[c]] : make_double2(0.0, 0.0);
-        }
-        for (int e = tid; e < p.TJ * kTC; e += kTraceThreads) {
-            const int r = e / kTC, c = e % kTC;
-            Bs[r][c] = (c < nt) ? psi[row_j[r] | toff[c]] : make_double2(0.0, 0.0);
-        }
-        __syncthreads();
-        for (int c = lane_t; c < kTC; c += p.LT) {
-            const double2 x = As[oi][c], y = Bs[oj][c];
-            // x * conj(y)
-            accr = fma(x.x, y.x, fma(x.y, y.y, accr));
-            acci = fma(x.y, y.x, fma(-x.x, y.y, acci));
-        }
+    double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += 4) {
+        const bool vt = t0 + kk < t_end;
+        double2 x = make_double2(0.0, 0.0), y = make_double2(0.0, 0.0);
+        if (vi && vt) x = psi[row_i | toff];
+        if (vj && vt) y = psi[row_j | toff];
+        dmma_m8n8k4(re0, re1, x.x, y.x);
+        dmma_m8n8k4(re0, re1, x.y, y.y);
+        dmma_m8n8k4(im0, im1, x.y, y.x);
+        dmma_m8n8k4(im0, im1, -x.x, y.y);
+        toff = ((toff | ~mask) + step4) & mask;
     }
-    red[tid] = make_double2(accr, acci);
-    __syncthreads();
-    if (lane_t == 0) {
-        for (int l = 1; l < p.LT; ++l) {
-            const double2 v = red[l * outs + o];
-            accr += v.x;
-            acci += v.y;
-        }
-        const int64_t D = (int64_t)1 << p.n_keep;
-        double2 *dst = p.out + (((int64_t)split * p.n_sets + set) * p.batch + b) * D * D;
-        dst[(int64_t)(ti0 + oi) * D + (tj0 + oj)] = make_double2(accr, acci);
-    }
+    // accumulator fragment: row lane/4, columns (lane%4)*2 + {0, 1}
+    double2 *dst = p.out + (((int64_t)split * p.n_sets + set) * p.batch + b) * D * D;
+    const int64_t col = (int64_t)J * 8 + kk * 2;
+    if (vi && col < D) dst[i * D + col] = make_double2(re0, im0);
+    if (vi && col + 1 < D) dst[i * D + col + 1] = make_double2(re1, im1);
 }
 
 __global__ void reduce_splits_kernel(const double2 *__restrict__ partial, double2 *__restrict__ out, int64_t count,
@@ -128,7 +121,7 @@ __global__ void reduce_splits_kernel(const double2 *__restrict__ partial, double
 
 namespace {
 struct TracePlan {
-    int TI, TJ, LT, tiles_i, tiles_j, splits;
+    int tiles, splits;
     int64_t t_per_split;
 };
 
@@ -136,22 +129,15 @@ TracePlan plan_trace(int n_keep, int n_trace, int batch, int n_sets, int sm_coun
 {
     TracePlan pl;
     const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_trace;
-    pl.TI = (int)std::min<int64_t>(D, 16);
-    pl.TJ = pl.TI;
-    pl.LT = kTraceThreads / (pl.TI * pl.TJ);
-    pl.tiles_i = (int)(D / pl.TI);
-    pl.tiles_j = pl.tiles_i;
-    const int64_t ctas = (int64_t)pl.tiles_i * pl.tiles_j * batch * n_sets;
-    const int64_t want = 2LL * sm_count;
-    int64_t splits = 1;
-    if (ctas < want) splits = (want + ctas - 1) / ctas;
-    const int64_t max_splits = std::max<int64_t>(1, T / 128);  // at least 128 traced indices per split
-    splits = std::min(splits, max_splits);
-    splits = std::min<int64_t>(splits, 1024);
+    pl.tiles = (int)((D + 7) / 8);
+    const int64_t base = (int64_t)pl.tiles * pl.tiles * batch * n_sets;  // warps without splitting
+    const int64_t want = 16LL * sm_count;                                // 16 warps per SM in flight
+    int64_t splits = base < want ? (want + base - 1) / base : 1;
+    splits = std::min(splits, std::max<int64_t>(1, T / 16));  // at least 4 MMA steps per split
+    splits = std::min<int64_t>(splits, 4096);
     int64_t per = (T + splits - 1) / splits;
-    per = (per + kTC - 1) / kTC * kTC;
-    splits = (T + per - 1) / per;
-    pl.splits = (int)splits;
+    per = (per + 3) / 4 * 4;
+    pl.splits = (int)((T + per - 1) / per);
     pl.t_per_split = per;
     return pl;
 }
@@ -180,17 +166,15 @@ cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, c
     p.batch = batch;
     p.n_sets = n_sets;
     p.splits = pl.splits;
-    p.TI = pl.TI;
-    p.TJ = pl.TJ;
-    p.LT = pl.LT;
-    p.tiles_i = pl.tiles_i;
-    p.tiles_j = pl.tiles_j;
+    p.tiles = pl.tiles;
     p.t_per_split = pl.t_per_split;
     p.out = (pl.splits > 1) ? partial : rho_out;
-    const int64_t zdim = (int64_t)batch * n_sets;
-    if (zdim > 65535 || (int64_t)pl.tiles_i * pl.tiles_j > 0x7fffffffLL) return cudaErrorInvalidValue;
-    dim3 grid(pl.tiles_i * pl.tiles_j, pl.splits, (unsigned)zdim);
-    trace_sv_kernel<<<grid, kTraceThreads, 0, st>>>(p);
+    const int64_t ydim = (int64_t)batch * n_sets;
+    const int64_t warps = (int64_t)pl.tiles * pl.tiles * pl.splits;
+    const int64_t xdim = (warps + kTraceWarps - 1) / kTraceWarps;
+    if (ydim > 65535 || xdim > 0x7fffffffLL) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)xdim, (unsigned)ydim);
+    trace_sv_dmma_kernel<<<grid, 32 * kTraceWarps, 0, st>>>(p);
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
