@@ -248,11 +248,30 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(obj) -> None:
+    """The ONE JSON line of this run, written to the process's original stdout."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
+    # Libraries (NCCL's version banner, torchrun warnings ...) like to chat on stdout; the contract is one JSON
+    # line there, so everything else that is written to fd 1 during the run goes to stderr instead.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,6 +292,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its version banner on stdout; keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     eng = get_engine(local)
@@ -459,7 +480,7 @@ def main():
                                              "nccl": "torch.distributed.gather (NCCL) to rank 0 inside the step",
                                              "none": "none (results stay sharded)"}[gather_mode],
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
