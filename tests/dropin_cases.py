@@ -167,6 +167,31 @@ def case_wigner_entry_points():
         wigner.wigner(rho, method="fft")
 
 
+def case_wigner_projections():
+    # wigner.py:290-375 -- qubit (|0>+|1>)/sqrt2 entangled with two coherent states of one 16-level qumode
+    qmr, qr, circuit = make_1mode_1qubit(nq_per_mode=4)
+    a0, a1 = an.coherent_amplitudes(1.0 + 0.5j, 16), an.coherent_amplitudes(-1.2j, 16)
+    x = np.concatenate([a0, a1]) / np.sqrt(2)  # qubit is the most significant bit
+    y_z = np.concatenate([a0, -a1]) / np.sqrt(2)  # Z on the qubit
+    y_x = np.concatenate([a1, a0]) / np.sqrt(2)  # X on the qubit
+    xvec = np.linspace(-5, 5, 96)
+    got = wigner.wigner_projections(circuit, Statevector(x), Statevector(y_z), Statevector(y_x), xvec)
+    want = []
+    for y in (y_z, y_x):
+        t = [partial_trace_sv(u * v.conj(), [4]) for u in (x, y) for v in (x, y)]  # xx, xy, yx, yy
+        want.append((t[0] + t[1] + t[2] + t[3]) / 4)
+        want.append((t[0] - t[1] - t[2] + t[3]) / 4)
+    assert len(got) == 4
+    for g, rho in zip(got, want):
+        ref = wigner_clenshaw(rho, xvec)
+        assert g.shape == (96, 96)
+        assert np.abs(g - ref).max() <= 1e-10 * max(np.abs(ref).max(), 1e-300)
+    # default grid is the reference's linspace(-6, 6, 200); unknown kwargs fail like _wigner(**kwargs) would
+    assert wigner.wigner_projections(circuit, x, y_z, y_x)[0].shape == (200, 200)
+    with pytest.raises(TypeError):
+        wigner.wigner_projections(circuit, x, y_z, y_x, bogus=1)
+
+
 def case_wigner_mle():
     rng = np.random.default_rng(3)
     base = an.coherent_amplitudes(1.0, 8)
