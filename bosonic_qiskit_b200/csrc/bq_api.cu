@@ -75,6 +75,8 @@ struct bq_handle_s {
     Buffer cs, partial, rho_tmp;                            // kernel scratch
     Buffer in_dev, out_dev, rho_dev, grid_dev, small_dev;   // staging for _host calls
     std::vector<double> grid_host;                          // what grid_dev currently holds
+    bool grid_host_mirror = false;                          // ... and whether it is a mirror-symmetric square grid
+    int grid_mode = 1;  // 0: never share recurrences, 1: _host calls test their grid, 2: + caller vouches for _dev grids
     unsigned int *ctr = nullptr;
     int ctr_next = 0;
     uint64_t launches = 0;
@@ -202,7 +204,8 @@ int check_method(int method)
 
 // device-side core: rho (device) -> W (device)
 int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
-                const double *d_x, int nx, const double *d_y, int ny, double g, double *d_W, cudaStream_t st)
+                const double *d_x, int nx, const double *d_y, int ny, double g, double *d_W, cudaStream_t st,
+                bool mirror_grid)
 {
     if (batch == 0 || nx == 0 || ny == 0) return BQ_OK;
     const double4 *tab = nullptr;
@@ -233,6 +236,7 @@ int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t 
     p.batch = batch;
     p.g = g;
     p.scale = g * g * 0.5 / 3.14159265358979323846;
+    p.sym = (mirror_grid && nx == ny && nx >= 2 && N >= 2) ? 1 : 0;
     p.ctr = h->ctr + 2 * h->ctr_next;
     h->ctr_next = (h->ctr_next + 1) % kCtrSlots;
     cudaEvent_t pa = nullptr, pb = nullptr;
@@ -264,6 +268,24 @@ int check_wigner_args(const void *rho, int N, int64_t ld, int64_t rho_stride, in
 }
 
 // uploads (xvec, yvec) unless the device copy already holds exactly these values
+// yvec == xvec and xvec[S-1-i] == -xvec[i] to within 4 ulp of max|x|: the grids wigner.py:135,187-188 builds
+// (numpy.linspace(-a, a, S) is symmetric to ~1 ulp, not bit-exactly).  The symmetric kernels take the mirrored
+// coordinate as exactly -x, which moves a grid point by at most that much.
+bool grid_is_mirror(const double *x, int nx, const double *y, int ny)
+{
+    if (nx != ny || nx < 2) return false;
+    double amax = 0.0;
+    for (int i = 0; i < nx; ++i) {
+        if (!(x[i] == y[i]) || !std::isfinite(x[i])) return false;
+        amax = std::max(amax, std::fabs(x[i]));
+    }
+    const double tol = 4.0 * 2.220446049250313e-16 * amax;
+    for (int i = 0; i < nx / 2; ++i)
+        if (std::fabs(x[i] + x[nx - 1 - i]) > tol) return false;
+    if ((nx & 1) && std::fabs(x[nx / 2]) > tol) return false;
+    return true;
+}
+
 int stage_grid(bq_handle_t h, const double *x, int nx, const double *y, int ny, const double **dx, const double **dy)
 {
     const size_t n = (size_t)nx + ny;
@@ -279,6 +301,7 @@ int stage_grid(bq_handle_t h, const double *x, int nx, const double *y, int ny, 
         std::memcpy(h->grid_host.data() + 2, x, sizeof(double) * nx);
         std::memcpy(h->grid_host.data() + 2 + nx, y, sizeof(double) * ny);
         if (n) CU(cudaMemcpy(h->grid_dev.ptr, h->grid_host.data() + 2, sizeof(double) * n, cudaMemcpyHostToDevice));
+        h->grid_host_mirror = grid_is_mirror(x, nx, y, ny);
     }
     *dx = (const double *)h->grid_dev.ptr;
     *dy = (const double *)h->grid_dev.ptr + nx;
@@ -659,7 +682,8 @@ int bq_wigner_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t
     DeviceGuard guard(h->dev.device);
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = order_stream(h, st))) return rc;
-    return wigner_core(h, (const double2 *)d_rho, N, ld, rho_stride, batch, d_xvec, nx, d_yvec, ny, g, d_W_out, st);
+    return wigner_core(h, (const double2 *)d_rho, N, ld, rho_stride, batch, d_xvec, nx, d_yvec, ny, g, d_W_out, st,
+                       h->grid_mode == 2);
 }
 
 int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t rho_stride, int batch,
@@ -678,7 +702,9 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
     const size_t in_elems = (size_t)((int64_t)(batch - 1) * rho_stride + (int64_t)(N - 1) * ld + N);
     const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
     CU(h->in_dev.reserve(in_elems * sizeof(double2)));
-    double *d_out = mapped_alias(W_out);
+    // the symmetric kernels scatter 8-byte stores over the grid: fine for HBM/L2, not for posted writes over PCIe
+    const bool mirror = h->grid_mode >= 1 && h->grid_host_mirror;
+    double *d_out = mirror ? nullptr : mapped_alias(W_out);
     const bool direct = d_out != nullptr;
     if (!direct) {
         CU(h->out_dev.reserve(out_b));
@@ -686,7 +712,8 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
     }
     HostTimer timer(h);
     CU(cudaMemcpyAsync(h->in_dev.ptr, rho, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-    rc = wigner_core(h, (const double2 *)h->in_dev.ptr, N, ld, rho_stride, batch, dx, nx, dy, ny, g, d_out, h->stream);
+    rc = wigner_core(h, (const double2 *)h->in_dev.ptr, N, ld, rho_stride, batch, dx, nx, dy, ny, g, d_out, h->stream,
+                     mirror);
     if (rc) return rc;
     if (!direct) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
     return timer.finish();
@@ -695,7 +722,7 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
 // ---- fused frame loop --------------------------------------------------------------------------
 static int state_to_wigner_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced,
                                 int batch, int64_t psi_stride, const double *dx, int nx, const double *dy, int ny,
-                                double g, double *d_W, double2 *d_rho_opt, cudaStream_t st)
+                                double g, double *d_W, double2 *d_rho_opt, cudaStream_t st, bool mirror_grid)
 {
     const int n_keep = n_qubits - n_traced;
     if (n_keep > 14) return fail(BQ_ERR_INVALID, "reduced density matrix larger than 2^14 x 2^14");
@@ -707,7 +734,7 @@ static int state_to_wigner_core(bq_handle_t h, const double2 *d_psi, int n_qubit
     }
     int rc = trace_sv_core(h, d_psi, n_qubits, traced, n_traced, 1, batch, psi_stride, d_rho, st);
     if (rc) return rc;
-    return wigner_core(h, d_rho, (int)D, D, D * D, batch, dx, nx, dy, ny, g, d_W, st);
+    return wigner_core(h, d_rho, (int)D, D, D * D, batch, dx, nx, dy, ny, g, d_W, st, mirror_grid);
 }
 
 int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
@@ -727,7 +754,7 @@ int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, con
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = order_stream(h, st))) return rc;
     return state_to_wigner_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, batch, psi_stride, d_xvec, nx,
-                                d_yvec, ny, g, d_W_out, (double2 *)d_rho_out, st);
+                                d_yvec, ny, g, d_W_out, (double2 *)d_rho_out, st, h->grid_mode == 2);
 }
 
 int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
@@ -752,7 +779,8 @@ int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, cons
     const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
     const size_t rho_b = (size_t)batch * D * D * sizeof(double2);
     CU(h->in_dev.reserve(in_elems * sizeof(double2)));
-    double *d_out = out_b ? mapped_alias(W_out) : nullptr;
+    const bool mirror = h->grid_mode >= 1 && h->grid_host_mirror;
+    double *d_out = (out_b && !mirror) ? mapped_alias(W_out) : nullptr;
     const bool direct = d_out != nullptr;
     if (!direct) {
         CU(h->out_dev.reserve(std::max<size_t>(out_b, 8)));
@@ -762,7 +790,7 @@ int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, cons
     HostTimer timer(h);
     CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, batch, psi_stride, dx, nx,
-                              dy, ny, g, d_out, (double2 *)h->rho_dev.ptr, h->stream);
+                              dy, ny, g, d_out, (double2 *)h->rho_dev.ptr, h->stream, mirror);
     if (rc) return rc;
     if (rho_out) CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, rho_b, cudaMemcpyDeviceToHost, h->stream));
     if (out_b && !direct) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
@@ -825,6 +853,21 @@ int bq_last_device_ms(bq_handle_t h, double *ms)
     if (!h || !ms) return fail(BQ_ERR_INVALID, "NULL argument");
     *ms = h->last_ms;
     return BQ_OK;
+}
+
+int bq_set_grid_symmetry(bq_handle_t h, int mode)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (mode < 0 || mode > 2) return fail(BQ_ERR_INVALID, "grid symmetry mode must be 0, 1 or 2");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->grid_mode = mode;
+    return BQ_OK;
+}
+
+int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny)
+{
+    if (nx < 0 || ny < 0 || ((nx > 0 || ny > 0) && (!xvec || !yvec))) return 0;
+    return grid_is_mirror(xvec, nx, yvec, ny) ? 1 : 0;
 }
 
 int bq_set_sass_mode(bq_handle_t h, int mode, int *active)

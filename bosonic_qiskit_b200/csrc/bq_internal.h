@@ -8,7 +8,7 @@ namespace bq {
 
 constexpr int kResidentMaxN = 64;  // stream fits twice per SM in shared memory up to this cutoff
 constexpr int kMaxQubits = 40;
-constexpr int kKernelSlots = 16;
+constexpr int kKernelSlots = 32;
 
 // records in the coefficient stream of cutoff N, and the first record of the diagonal with K = N-L
 // coefficients (K >= 2); layout described in bq_common.cuh
@@ -37,6 +37,9 @@ struct WigParams {
     int chunks_per_row, tiles_per_frame, total_tiles, grab, vec_ok;
     double g, scale;
     unsigned int *ctr;  // [0] next tile, [1] CTAs that left
+    // mirror-symmetric grids (wigner_sym_* kernels): U = ceil(S/2) mirror classes, U(U+1)/2 units per frame
+    int sym, sym_U;
+    int64_t sym_units;
 };
 
 struct TraceMap {

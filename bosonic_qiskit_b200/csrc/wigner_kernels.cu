@@ -443,6 +443,277 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_diag_kernel(const WigParams
 }
 
 // ------------------------------------------------------------------------------------------------
+// Mirror-symmetric grids (yvec == xvec, xvec[S-1-i] == -xvec[i]): radial sharing of the inner recurrence.
+//
+// The inner Clenshaw sum S_L depends on the grid point only through B = g^2 (x^2 + p^2); only the outer Horner
+// step sees A2 = g (x + i p).  On the grids the reference always builds (wigner.py:135 `xvec = linspace(-a, a, S)`,
+// wigner.py:187-188 `yvec = xvec`) the eight points (+-x_a, +-x_b), (+-x_b, +-x_a) share B, so one thread runs
+// ONE recurrence per unordered pair {a, b} of grid lines and eight Horner accumulators: 5 N^2 / 2 flops per pair
+// instead of per point (6.5x fewer fp64 instructions at N = 64, 7.9x at N = 1024).  Same coefficient stream,
+// same step, same rounding of every S_L; the only differences to the point-by-point kernels are that B comes
+// from the pair's representative (x_a, x_b) -- the mirrored coordinate is taken as exactly -x_a, the host
+// checks |x[S-1-i] + x[i]| <= 4 ulp before choosing this path -- and that A2 is scaled by 1/sqrt(L+1) before
+// the complex multiply instead of after (one rounding moved).  Both are at the 1e-16 level.
+//
+// A unit is a pair (a <= b) of the U = ceil(S/2) mirror classes, numbered row by row (row a holds b = a..U-1);
+// a thread owns CL consecutive units.  Degenerate units (a == b, or the middle line of an odd grid) simply
+// write the same value twice.
+// ------------------------------------------------------------------------------------------------
+template <int CL>
+struct SymPoints {
+    double B[CL], al[CL], be[CL];
+    double y0r[CL], y0i[CL], y1r[CL], y1i[CL];
+    double wr[CL][8], wi[CL][8];
+};
+
+template <int CL>
+__device__ __forceinline__ void sym_step(SymPoints<CL> &s, const double2 c, const double4 t)
+{
+#pragma unroll
+    for (int p = 0; p < CL; ++p) {
+        const double tn = fma(s.B[p], t.z, t.y);
+        const double n0r = fma(t.x, s.y1r[p], c.x);
+        const double n0i = fma(t.x, s.y1i[p], c.y);
+        const double n1r = fma(tn, s.y1r[p], s.y0r[p]);
+        const double n1i = fma(tn, s.y1i[p], s.y0i[p]);
+        s.y0r[p] = n0r;
+        s.y0i[p] = n0i;
+        s.y1r[p] = n1r;
+        s.y1i[p] = n1i;
+    }
+}
+
+// point k of a unit:  k < 4: A2 = (s1 be, s2 al) -> W[iy = a or S-1-a][ix = b or S-1-b];  k >= 4: the transpose.
+// s1 = -1 for odd k, s2 = -1 for k & 2.
+template <int CL>
+__device__ __forceinline__ void sym_tail(SymPoints<CL> &s, const double4 t)
+{
+#pragma unroll
+    for (int p = 0; p < CL; ++p) {
+        const double tn = fma(s.B[p], t.z, t.y);
+        const double Sr = fma(tn, s.y1r[p], s.y0r[p]);
+        const double Si = fma(tn, s.y1i[p], s.y0i[p]);
+        const double as = s.al[p] * t.z, bs = s.be[p] * t.z;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double pr = (k & 1) ? -((k < 4) ? bs : as) : ((k < 4) ? bs : as);
+            const double pi = (k & 2) ? -((k < 4) ? as : bs) : ((k < 4) ? as : bs);
+            const double wr = s.wr[p][k], wi = s.wi[p][k];
+            s.wr[p][k] = fma(wr, pr, fma(-wi, pi, Sr));
+            s.wi[p][k] = fma(wr, pi, fma(wi, pr, Si));
+        }
+    }
+}
+
+template <int CL>
+__device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__restrict__ cd,
+                                             const double4 *__restrict__ td, const int K)
+{
+    {
+        const double2 c1 = cd[0], c0 = cd[1];
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+            s.y1r[k] = c1.x;
+            s.y1i[k] = c1.y;
+            s.y0r[k] = c0.x;
+            s.y0i[k] = c0.y;
+        }
+    }
+    const double2 *cp = cd + 2;
+    const double4 *tp = td + 2;
+    const int m = K - 2;
+    int r = 0;
+    for (; r + 1 < m; r += 2) {
+        sym_step<CL>(s, cp[r], tp[r]);
+        sym_step<CL>(s, cp[r + 1], tp[r + 1]);
+    }
+    if (r < m) sym_step<CL>(s, cp[r], tp[r]);
+    sym_tail<CL>(s, tp[m]);
+}
+
+// unit index -> (a, b), a <= b < U;  row a starts at a U - a (a - 1) / 2
+__device__ __forceinline__ void sym_unit(int64_t t, int U, int &a, int &b)
+{
+    const double w = 2.0 * U + 1.0;
+    int r = (int)((w - sqrt(w * w - 8.0 * (double)t)) * 0.5);
+    r = max(0, min(r, U - 1));
+    while (r > 0 && (int64_t)r * U - (int64_t)r * (r - 1) / 2 > t) --r;
+    while (r + 1 < U && (int64_t)(r + 1) * U - (int64_t)(r + 1) * r / 2 <= t) ++r;
+    a = r;
+    b = r + (int)(t - ((int64_t)r * U - (int64_t)r * (r - 1) / 2));
+}
+
+template <int CL>
+__device__ __forceinline__ void sym_load(const WigParams &p, int64_t chunk, SymPoints<CL> &s, int (&ua)[CL], int (&ub)[CL],
+                                         const double2 h)
+{
+#pragma unroll
+    for (int c = 0; c < CL; ++c) {
+        const int64_t t = min(chunk * CL + c, p.sym_units - 1);
+        sym_unit(t, p.sym_U, ua[c], ub[c]);
+        s.al[c] = p.g * __ldg(p.xvec + ua[c]);
+        s.be[c] = p.g * __ldg(p.xvec + ub[c]);
+        s.B[c] = fma(s.be[c], s.be[c], s.al[c] * s.al[c]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s.wr[c][k] = h.x;
+            s.wi[c][k] = h.y;
+        }
+    }
+}
+
+template <int CL>
+__device__ __forceinline__ void sym_store(const WigParams &p, int frame, int64_t chunk, const SymPoints<CL> &s,
+                                          const int (&ua)[CL], const int (&ub)[CL])
+{
+    double *Wf = p.W + (int64_t)frame * p.w_stride;
+    const int S = p.nx;
+#pragma unroll
+    for (int c = 0; c < CL; ++c) {
+        if (chunk * CL + c >= p.sym_units) continue;
+        const double e = exp(-0.5 * s.B[c]) * p.scale;
+        const int a = ua[c], b = ub[c], am = S - 1 - a, bm = S - 1 - b;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i1 = (k & 1) ? ((k < 4) ? bm : am) : ((k < 4) ? b : a);   // ix
+            const int i2 = (k & 2) ? ((k < 4) ? am : bm) : ((k < 4) ? a : b);   // iy
+            Wf[(int64_t)i2 * S + i1] = s.wr[c][k] * e;
+        }
+    }
+}
+
+template <int CL, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) wigner_sym_resident_kernel(const WigParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)p.R_tot * 32);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.R_tot * 48);
+    int *slot = reinterpret_cast<int *>(bar + 1);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    int loaded_frame = -1;
+    TileCursor tc{0, 0};
+    const int N = p.N;
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        if (frame != loaded_frame) {
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
+                const bool first = loaded_frame < 0;
+                mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
+                if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
+                bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            loaded_frame = frame;
+        }
+        SymPoints<CL> s;
+        int ua[CL], ub[CL];
+        const int64_t chunk = (int64_t)tif * THREADS + tid;
+        sym_load<CL>(p, chunk, s, ua, ub, cs_s[0]);
+        int pos = 1;
+        for (int K = 2; K <= N; ++K) {
+            sym_diagonal<CL>(s, cs_s + pos, tab_s + pos, K);
+            pos += K + 1;
+        }
+        sym_store<CL>(p, frame, chunk, s, ua, ub);
+    }
+    leave_grid(p);
+}
+
+template <int CL, int THREADS, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigParams p)
+{
+    constexpr int NWARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = p.N, cap = N + 1;
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)STAGES * cap * 32);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * cap * 48);
+    uint64_t *empty = full + STAGES;
+    int *slot = reinterpret_cast<int *>(empty + STAGES);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t full_phase = 0, fill_count = 0;
+    TileCursor tc{0, 0};
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
+
+        int pg = 0, pK = 2;
+        auto produce = [&]() {
+            const uint32_t st = (uint32_t)pg % STAGES;
+            const int Kend = group_end(pK, pg == 0, cap, N);
+            const int64_t first = (pg == 0) ? 0 : diag_pos(pK);
+            const int64_t last = (Kend <= N) ? diag_pos(Kend) : (int64_t)p.R_tot;
+            const uint32_t recs = (uint32_t)(last - first);
+            mbar_wait(&empty[st], ((fill_count >> st) & 1u) ^ 1u);
+            fill_count ^= 1u << st;
+            mbar_arrive_expect_tx(&full[st], recs * 48u);
+            bulk_g2s(tab_s + (size_t)st * cap, p.tab + first, recs * 32u, &full[st]);
+            bulk_g2s(cs_s + (size_t)st * cap, cs_g + first, recs * 16u, &full[st]);
+            ++pg;
+            pK = Kend;
+        };
+        if (tid == 0)
+            for (int d = 0; d < STAGES - 1 && pK <= N; ++d) produce();
+
+        SymPoints<CL> s;
+        int ua[CL], ub[CL];
+        const int64_t chunk = (int64_t)tif * THREADS + tid;
+        bool loaded = false;
+
+        int K = 2;
+        for (int g = 0; K <= N; ++g) {
+            const uint32_t st = (uint32_t)g % STAGES;
+            mbar_wait(&full[st], (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            const double2 *cb = cs_s + (size_t)st * cap;
+            const double4 *tb = tab_s + (size_t)st * cap;
+            int pos = 0;
+            if (!loaded) {
+                sym_load<CL>(p, chunk, s, ua, ub, cb[0]);
+                loaded = true;
+                pos = 1;
+            }
+            const int Kend = group_end(K, g == 0, cap, N);
+            for (; K < Kend; ++K) {
+                sym_diagonal<CL>(s, cb + pos, tb + pos, K);
+                pos += K + 1;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+            if (tid == 0 && pK <= N) produce();
+        }
+        sym_store<CL>(p, frame, chunk, s, ua, ub);
+    }
+    leave_grid(p);
+}
+
+// ------------------------------------------------------------------------------------------------
 // N > 64: coefficient stream pulled through a shared-memory ring by bulk copies
 // ------------------------------------------------------------------------------------------------
 template <int PTS, int THREADS, int STAGES, int CHUNK>
@@ -578,7 +849,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 8;
+constexpr int kVariants = 11;
 constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
@@ -590,6 +861,9 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_resident_kernelILi8ELi128ELi2EEEvNS_9WigParamsE",
     "_ZN2bq20wigner_stream_kernelILi8ELi128ELi4ELi256EEEvNS_9WigParamsE",
     "_ZN2bq18wigner_diag_kernelILi8ELi256ELi3EEEvNS_9WigParamsE",
+    "_ZN2bq26wigner_sym_resident_kernelILi3ELi128ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq26wigner_sym_resident_kernelILi1ELi128ELi4EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_sym_diag_kernelILi3ELi256ELi3EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -623,7 +897,7 @@ const Patched &patched_kernels()
 }
 
 cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigParams &p, int pts, DeviceInfo &dev,
-                cudaStream_t st, int *launches)
+                cudaStream_t st, int *launches, int64_t sym_chunks = -1)
 {
     const bool use_patched = dev.sass_mode != 0 && patched_kernels().ok;
     const void *func = use_patched ? patched_kernels().func[variant] : plain;
@@ -643,7 +917,8 @@ cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigPar
         dev.occ_smem[slot] = smem;
     }
     p.chunks_per_row = (p.nx + pts - 1) / pts;
-    const int64_t chunks = (int64_t)p.chunks_per_row * p.ny;
+    // work items per frame: runs of `pts` points of one row, or (symmetric grids) runs of `pts` units
+    const int64_t chunks = sym_chunks >= 0 ? sym_chunks : (int64_t)p.chunks_per_row * p.ny;
     const int64_t tpf = (chunks + threads - 1) / threads;
     if (tpf * p.batch > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.tiles_per_frame = (int)tpf;
@@ -668,6 +943,24 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
     const int64_t points = (int64_t)p.nx * p.ny * p.batch;
     if (points == 0) return cudaSuccess;
     const int64_t want = 2LL * dev.sm_count;  // tiles needed before the big tile pays off
+    if (p.sym) {
+        // mirror-symmetric grid (the caller checked it): one recurrence per pair of grid lines
+        p.sym_U = (p.nx + 1) / 2;
+        p.sym_units = (int64_t)p.sym_U * (p.sym_U + 1) / 2;
+        const int64_t units = p.sym_units * p.batch;
+        if (p.N <= kResidentMaxN) {
+            const size_t smem = (size_t)p.R_tot * 48 + 64;
+            if (units >= 3LL * 128 * dev.sm_count)
+                return run((const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 128, smem, p, 3, dev, st, launches,
+                           (p.sym_units + 2) / 3);
+            return run((const void *)wigner_sym_resident_kernel<1, 128, 4>, 9, 128, smem, p, 1, dev, st, launches, p.sym_units);
+        }
+        const size_t smem_diag = (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
+        if (smem_diag <= dev.smem_optin && units >= 3LL * 256 * (dev.sm_count / 2))
+            return run((const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 256, smem_diag, p, 3, dev, st, launches,
+                       (p.sym_units + 2) / 3);
+        p.sym = 0;  // too few units (or too large a cutoff) for the ring kernel: point-by-point kernels below
+    }
     if (p.N <= kResidentMaxN) {
         const size_t base = (size_t)p.R_tot * 48 + 64;  // + staging buffer of the tile's bulk store
         const size_t smem = base + 1024 * sizeof(double);

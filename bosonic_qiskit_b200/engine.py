@@ -70,6 +70,9 @@ class Engine:
         self._pool: dict[int, list[int]] = {}
         self._pool_bytes = 0
         self._pool_lock = threading.Lock()
+        self._grid_lock = threading.Lock()
+        self._grid_sharing = True
+        self._grid_verdicts: dict[tuple, bool] = {}
 
     def close(self) -> None:
         self._finalizer()
@@ -100,6 +103,35 @@ class Engine:
         active = ctypes.c_int()
         check(self._lib.bq_set_sass_mode(self._h, 1 if patched else 0, ctypes.byref(active)))
         return bool(active.value)
+
+    def set_grid_sharing(self, on: bool) -> None:
+        """Mirror-symmetric grids (``yvec == xvec == -xvec[::-1]``, what the reference always builds): share the
+        inner Clenshaw recurrence between the eight points of equal ``x**2 + p**2`` (default on).  Off = always the
+        point-by-point kernels."""
+        with self._grid_lock:
+            self._grid_sharing = bool(on)
+            check(self._lib.bq_set_grid_symmetry(self._h, 1 if on else 0))
+
+    def grid_is_mirror(self, xvec, yvec=None) -> bool:
+        """The library's own test of a host grid (``bq_grid_is_mirror``)."""
+        x = _f64(xvec).reshape(-1)
+        y = x if yvec is None else _f64(yvec).reshape(-1)
+        return bool(self._lib.bq_grid_is_mirror(_ptr(x), len(x), _ptr(y), len(y)))
+
+    def _device_grid_mode(self, xvec, yvec) -> int:
+        """Grid-symmetry mode for a ``_dev`` call: the library cannot read a device grid without a synchronisation,
+        so the binding tests each grid tensor once (keyed on storage, size and torch's version counter)."""
+        if not self._grid_sharing:
+            return 0
+        key = (xvec.data_ptr(), xvec.numel(), xvec._version, yvec.data_ptr(), yvec.numel(), yvec._version)
+        verdict = self._grid_verdicts.get(key)
+        if verdict is None:
+            if len(self._grid_verdicts) > 64:
+                self._grid_verdicts.clear()
+            xh = xvec.detach().cpu().numpy()
+            yh = xh if yvec is xvec else yvec.detach().cpu().numpy()
+            verdict = self._grid_verdicts[key] = self.grid_is_mirror(xh, yh)
+        return 2 if verdict else 1
 
     def profile(self, on: bool) -> None:
         """Bracket every Wigner-kernel launch with CUDA events (bench.py's roofline leg)."""
@@ -288,10 +320,12 @@ class Engine:
             out = torch.empty((batch, yvec.numel(), xvec.numel()), dtype=torch.float64, device=rho.device)
         else:
             self._check_tensor(out, torch.float64, "out")
-        check(self._lib.bq_wigner_dev(self._h, ctypes.c_void_p(rho3.data_ptr()), N, N, N * N, batch,
-                                      ctypes.c_void_p(xvec.data_ptr()), xvec.numel(),
-                                      ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g), code,
-                                      ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+        with self._grid_lock:
+            check(self._lib.bq_set_grid_symmetry(self._h, self._device_grid_mode(xvec, yvec)))
+            check(self._lib.bq_wigner_dev(self._h, ctypes.c_void_p(rho3.data_ptr()), N, N, N * N, batch,
+                                          ctypes.c_void_p(xvec.data_ptr()), xvec.numel(),
+                                          ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g), code,
+                                          ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
         return out[0] if single else out
 
     def partial_trace_sv_t(self, psi, traced: Sequence[int], out=None, stream=None):
@@ -334,11 +368,16 @@ class Engine:
             out_ptr = out  # raw device pointer (e.g. a peer buffer)
         else:
             out_ptr = out.data_ptr()
-        check(self._lib.bq_state_to_wigner_dev(
-            self._h, ctypes.c_void_p(psi2.data_ptr()), n, _int_array(traced), len(traced), batch, dim,
-            ctypes.c_void_p(xvec.data_ptr()), xvec.numel(), ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g),
-            code, ctypes.c_void_p(out_ptr), ctypes.c_void_p(rho_out.data_ptr()) if rho_out is not None else None,
-            self._stream_ptr(stream)))
+        with self._grid_lock:
+            # a raw output pointer is a peer GPU's buffer: keep the contiguous bulk stores of the point-by-point
+            # kernels on that path (the symmetric kernels scatter 8-byte stores)
+            mode = self._device_grid_mode(xvec, yvec) if not isinstance(out, int) else min(1, int(self._grid_sharing))
+            check(self._lib.bq_set_grid_symmetry(self._h, mode))
+            check(self._lib.bq_state_to_wigner_dev(
+                self._h, ctypes.c_void_p(psi2.data_ptr()), n, _int_array(traced), len(traced), batch, dim,
+                ctypes.c_void_p(xvec.data_ptr()), xvec.numel(), ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g),
+                code, ctypes.c_void_p(out_ptr), ctypes.c_void_p(rho_out.data_ptr()) if rho_out is not None else None,
+                self._stream_ptr(stream)))
         if isinstance(out, int):
             return None
         return out[0] if single else out

@@ -146,6 +146,20 @@ int bq_profile_enable(bq_handle_t h, int on);
 int bq_set_sass_mode(bq_handle_t h, int mode, int *active);
 int bq_profile_read(bq_handle_t h, double *total_ms, int *launches);
 
+/* ---- mirror-symmetric grids ------------------------------------------------------------------
+ * The reference only ever evaluates W on `xvec = linspace(-a, a, S)`, `yvec = xvec`
+ * (src/bosonic_qiskit/wigner.py:135,187-188).  On such a grid the eight points (+-x_a, +-x_b),
+ * (+-x_b, +-x_a) share |A2|^2, hence the whole inner Clenshaw recurrence; the library then runs one
+ * recurrence per pair of grid lines and eight Horner accumulators (same results to ~1e-15, 6-8x fewer
+ * fp64 instructions).  mode 0: never (always the point-by-point kernels); mode 1 (default): the `_host`
+ * entry points test the grid they are given (bq_grid_is_mirror), the `_dev` entry points -- which cannot
+ * read a device grid without a synchronisation -- use the point-by-point kernels; mode 2: as 1, and the
+ * caller vouches that the grids passed to `_dev` entry points are mirror-symmetric with yvec == xvec
+ * until the mode is changed (the Python binding tests device grids once and caches the verdict).      */
+int bq_set_grid_symmetry(bq_handle_t h, int mode);
+/* 1 if nx == ny >= 2, yvec[i] == xvec[i] and |xvec[i] + xvec[nx-1-i]| <= 4 ulp of max|xvec|; else 0 */
+int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny);
+
 /* ---- CUDA IPC plumbing for the multi-GPU tile gather ---------------------------------------- */
 /* One process per GPU: the root exports its gather buffer, peers open it and let the Wigner
  * kernel store finished tiles straight into it over NVLink (replaces the pickled return of
