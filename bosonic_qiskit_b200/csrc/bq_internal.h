@@ -21,6 +21,7 @@ struct DeviceInfo {
     size_t smem_optin = 0;
     // per-kernel launch cache (attribute set once, occupancy looked up once per shared-memory size)
     int pts8 = 0;       // use the 8-points-per-thread resident kernel for large grids
+    int sym_force = -1; // >= 0: tuning aid (env BQ_B200_SYM_VARIANT), only this symmetric-kernel variant is eligible
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     bool configured[kKernelSlots] = {};
     int occ[kKernelSlots] = {};

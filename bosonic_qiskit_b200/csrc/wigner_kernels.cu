@@ -849,7 +849,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 11;
+constexpr int kVariants = 16;
 constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
@@ -864,6 +864,11 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq26wigner_sym_resident_kernelILi3ELi128ELi2EEEvNS_9WigParamsE",
     "_ZN2bq26wigner_sym_resident_kernelILi1ELi128ELi4EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_sym_diag_kernelILi3ELi256ELi3EEEvNS_9WigParamsE",
+    "_ZN2bq26wigner_sym_resident_kernelILi2ELi128ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq26wigner_sym_resident_kernelILi2ELi192ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq26wigner_sym_resident_kernelILi1ELi256ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_sym_diag_kernelILi2ELi256ELi3EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_sym_diag_kernelILi2ELi384ELi3EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -896,8 +901,10 @@ const Patched &patched_kernels()
     return pk;
 }
 
-cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigParams &p, int pts, DeviceInfo &dev,
-                cudaStream_t st, int *launches, int64_t sym_chunks = -1)
+// resident CTAs per SM of one kernel variant at this shared-memory size (cached per device); also resolves which
+// machine code (re-scheduled or nvcc's) the variant launches
+cudaError_t occupancy(const void *plain, int variant, int threads, size_t smem, DeviceInfo &dev, const void **func_out,
+                      int *occ_out)
 {
     const bool use_patched = dev.sass_mode != 0 && patched_kernels().ok;
     const void *func = use_patched ? patched_kernels().func[variant] : plain;
@@ -916,6 +923,18 @@ cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigPar
         dev.occ[slot] = occ;
         dev.occ_smem[slot] = smem;
     }
+    *func_out = func;
+    *occ_out = dev.occ[slot];
+    return cudaSuccess;
+}
+
+cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigParams &p, int pts, DeviceInfo &dev,
+                cudaStream_t st, int *launches, int64_t sym_chunks = -1)
+{
+    const void *func = nullptr;
+    int occ_now = 0;
+    cudaError_t e = occupancy(plain, variant, threads, smem, dev, &func, &occ_now);
+    if (e != cudaSuccess) return e;
     p.chunks_per_row = (p.nx + pts - 1) / pts;
     // work items per frame: runs of `pts` points of one row, or (symmetric grids) runs of `pts` units
     const int64_t chunks = sym_chunks >= 0 ? sym_chunks : (int64_t)p.chunks_per_row * p.ny;
@@ -924,7 +943,7 @@ cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigPar
     p.tiles_per_frame = (int)tpf;
     p.total_tiles = (int)(tpf * p.batch);
     p.vec_ok = (p.nx % pts == 0) && (((uintptr_t)p.W % 16u) == 0) && (pts % 2 == 0);
-    const int resident = dev.occ[slot] * dev.sm_count;
+    const int resident = occ_now * dev.sm_count;
     const int grid = (int)min((int64_t)resident, (int64_t)p.total_tiles);
     p.grab = max(1, p.total_tiles / (grid * 8));
     void *args[] = {(void *)&p};
@@ -948,17 +967,57 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         p.sym_U = (p.nx + 1) / 2;
         p.sym_units = (int64_t)p.sym_U * (p.sym_U + 1) / 2;
         const int64_t units = p.sym_units * p.batch;
-        if (p.N <= kResidentMaxN) {
-            const size_t smem = (size_t)p.R_tot * 48 + 64;
-            if (units >= 3LL * 128 * dev.sm_count)
-                return run((const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 128, smem, p, 3, dev, st, launches,
-                           (p.sym_units + 2) / 3);
-            return run((const void *)wigner_sym_resident_kernel<1, 128, 4>, 9, 128, smem, p, 1, dev, st, launches, p.sym_units);
+        // Variants differ in units per thread (CL) and warps per SM.  The work is known exactly, so the choice is
+        // by predicted duration: rounds of resident CTAs x units per thread / how well the variant keeps the fp64
+        // pipe busy (measured, tools/roofline_sweep.py --sharing on).  A 1024 x 1024 grid has 131 328 units = 1.16
+        // rounds of the 3-unit tile on 296 CTAs but 1.73 rounds of the 2-unit tile: the latter finishes first.
+        struct SymVariant {
+            const void *plain;
+            int variant, cl, threads;
+            double eff;
+        };
+        static const SymVariant resident_variants[] = {
+            {(const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 3, 128, 1.00},
+            {(const void *)wigner_sym_resident_kernel<2, 192, 2>, 12, 2, 192, 0.97},
+            {(const void *)wigner_sym_resident_kernel<2, 128, 2>, 11, 2, 128, 0.92},
+            {(const void *)wigner_sym_resident_kernel<1, 256, 2>, 13, 1, 256, 0.80},
+            {(const void *)wigner_sym_resident_kernel<1, 128, 4>, 9, 1, 128, 0.75},
+        };
+        static const SymVariant ring_variants[] = {
+            {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
+            {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 0.97},
+            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.90},
+        };
+        const bool resident = p.N <= kResidentMaxN;
+        const size_t smem = resident ? (size_t)p.R_tot * 48 + 64 : (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
+        const SymVariant *vars = resident ? resident_variants : ring_variants;
+        const int nvars = resident ? 5 : 3;
+        const SymVariant *best = nullptr;
+        double best_cost = 0.0;
+        if (smem <= dev.smem_optin && (resident || units >= 2LL * 256 * (dev.sm_count / 2))) {
+            for (int i = 0; i < nvars; ++i) {
+                const SymVariant &v = vars[i];
+                if (dev.sym_force >= 0 && v.variant != dev.sym_force) continue;
+                const void *func = nullptr;
+                int occ = 0;
+                if (occupancy(v.plain, v.variant, v.threads, smem, dev, &func, &occ) != cudaSuccess) {
+                    cudaGetLastError();
+                    continue;
+                }
+                const int64_t tiles = (((p.sym_units + v.cl - 1) / v.cl + v.threads - 1) / v.threads) * p.batch;
+                const int64_t ctas = (int64_t)occ * dev.sm_count;
+                const int64_t rounds = (tiles + ctas - 1) / ctas;
+                // a last round that fills only part of the machine still costs a whole tile
+                const double cost = (double)rounds * v.cl * v.threads * occ / v.eff;
+                if (!best || cost < best_cost) {
+                    best = &v;
+                    best_cost = cost;
+                }
+            }
         }
-        const size_t smem_diag = (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
-        if (smem_diag <= dev.smem_optin && units >= 3LL * 256 * (dev.sm_count / 2))
-            return run((const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 256, smem_diag, p, 3, dev, st, launches,
-                       (p.sym_units + 2) / 3);
+        if (best)
+            return run(best->plain, best->variant, best->threads, smem, p, best->cl, dev, st, launches,
+                       (p.sym_units + best->cl - 1) / best->cl);
         p.sym = 0;  // too few units (or too large a cutoff) for the ring kernel: point-by-point kernels below
     }
     if (p.N <= kResidentMaxN) {
