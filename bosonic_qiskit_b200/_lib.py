@@ -57,6 +57,7 @@ SIGNATURES = {
     "bq_ipc_export": (c_int, [_H, c_void_p, c_void_p]),
     "bq_ipc_open": (c_int, [_H, c_void_p, POINTER(c_void_p)]),
     "bq_ipc_close": (c_int, [_H, c_void_p]),
+    "bq_memcpy_dev": (c_int, [_H, c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 BQ_OK, BQ_ERR_INVALID, BQ_ERR_CUDA, BQ_ERR_NO_DEVICE, BQ_ERR_UNSUPPORTED = 0, -1, -2, -3, -4

@@ -857,6 +857,17 @@ int bq_last_device_ms(bq_handle_t h, double *ms)
     return BQ_OK;
 }
 
+int bq_memcpy_dev(bq_handle_t h, void *d_dst, const void *d_src, size_t bytes, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (bytes == 0) return BQ_OK;
+    if (!d_dst || !d_src) return fail(BQ_ERR_INVALID, "NULL pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return BQ_OK;
+}
+
 int bq_set_grid_symmetry(bq_handle_t h, int mode)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");

@@ -73,6 +73,7 @@ class Engine:
         self._grid_lock = threading.Lock()
         self._grid_sharing = True
         self._grid_verdicts: dict[tuple, bool] = {}
+        self._stage = None  # local block for symmetric-grid results bound for a peer buffer
 
     def close(self) -> None:
         self._finalizer()
@@ -361,6 +362,7 @@ class Engine:
         self._check_tensor(xvec, torch.float64, "xvec")
         self._check_tensor(yvec, torch.float64, "yvec")
         out_ptr = None
+        stage = None
         if out is None:
             out = torch.empty((batch, yvec.numel(), xvec.numel()), dtype=torch.float64, device=psi.device)
             out_ptr = out.data_ptr()
@@ -369,15 +371,25 @@ class Engine:
         else:
             out_ptr = out.data_ptr()
         with self._grid_lock:
-            # a raw output pointer is a peer GPU's buffer: keep the contiguous bulk stores of the point-by-point
-            # kernels on that path (the symmetric kernels scatter 8-byte stores)
-            mode = self._device_grid_mode(xvec, yvec) if not isinstance(out, int) else min(1, int(self._grid_sharing))
+            mode = self._device_grid_mode(xvec, yvec)
+            if isinstance(out, int) and mode == 2:
+                # A raw output pointer is a peer GPU's buffer.  The point-by-point kernels store finished tiles into
+                # it directly (contiguous bulk stores, fused compute + gather); the symmetric-grid kernels scatter
+                # 8-byte stores, so they fill a local block that then crosses NVLink as one copy on the same stream.
+                n_out = batch * yvec.numel() * xvec.numel()
+                if self._stage is None or self._stage.numel() < n_out or self._stage.device != psi.device:
+                    self._stage = torch.empty((n_out,), dtype=torch.float64, device=psi.device)
+                stage = self._stage
+                out_ptr = stage.data_ptr()
             check(self._lib.bq_set_grid_symmetry(self._h, mode))
             check(self._lib.bq_state_to_wigner_dev(
                 self._h, ctypes.c_void_p(psi2.data_ptr()), n, _int_array(traced), len(traced), batch, dim,
                 ctypes.c_void_p(xvec.data_ptr()), xvec.numel(), ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g),
                 code, ctypes.c_void_p(out_ptr), ctypes.c_void_p(rho_out.data_ptr()) if rho_out is not None else None,
                 self._stream_ptr(stream)))
+            if stage is not None:
+                check(self._lib.bq_memcpy_dev(self._h, ctypes.c_void_p(out), ctypes.c_void_p(out_ptr),
+                                              batch * yvec.numel() * xvec.numel() * 8, self._stream_ptr(stream)))
         if isinstance(out, int):
             return None
         return out[0] if single else out

@@ -171,6 +171,10 @@ int bq_device_free(bq_handle_t h, void *d_ptr);
 int bq_ipc_export(bq_handle_t h, void *d_ptr, unsigned char *handle64);
 int bq_ipc_open(bq_handle_t h, const unsigned char *handle64, void **d_ptr);
 int bq_ipc_close(bq_handle_t h, void *d_ptr);
+/* asynchronous device-to-device copy on `stream` (unified addressing: either side may be a peer GPU's buffer
+ * opened with bq_ipc_open).  Used when a finished block of grids was computed locally by the symmetric-grid
+ * kernels (scattered stores: kept inside the GPU) and then goes to the gather buffer as one NVLink copy.  */
+int bq_memcpy_dev(bq_handle_t h, void *d_dst, const void *d_src, size_t bytes, void *stream);
 
 #ifdef __cplusplus
 }

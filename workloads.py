@@ -136,3 +136,16 @@ CONFIGS = {"c1": config1, "c2": config2, "c3": config3, "c4": config4, "c5": con
 def flops_per_point(N: int) -> int:
     """Algorithmic fp64 flops per Wigner grid point at cutoff N."""
     return (N - 1) * (5 * N + 6) + 30
+
+
+def shared_units(S: int) -> int:
+    """Pairs of mirror classes of an S x S mirror-symmetric grid: one Clenshaw recurrence each (wigner_sym_* kernels)."""
+    U = (S + 1) // 2
+    return U * (U + 1) // 2
+
+
+def flops_per_unit_shared(N: int) -> int:
+    """fp64 flops the symmetric-grid kernels execute per unit (FMA = 2): 10 per inner step, and per diagonal the
+    closing S_L (6), the scaled A2 (2) and eight complex Horner updates (8 x 8); ~40 for exp / scale / B."""
+    return (N - 1) * (5 * (N - 2) + 72) + 40
+
