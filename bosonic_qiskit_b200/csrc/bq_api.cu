@@ -76,6 +76,7 @@ struct bq_handle_s {
     Buffer in_dev, out_dev, rho_dev, grid_dev, small_dev;   // staging for _host calls
     std::vector<double> grid_host;                          // what grid_dev currently holds
     bool grid_host_mirror = false;                          // ... and whether it is a mirror-symmetric square grid
+    int64_t unit_first = 0, unit_count = -1;                // bq_set_unit_range (count < 0: whole grid)
     int grid_mode = 1;  // 0: never share recurrences, 1: _host calls test their grid, 2: + caller vouches for _dev grids
     unsigned int *ctr = nullptr;
     int ctr_next = 0;
@@ -237,6 +238,10 @@ int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t 
     p.g = g;
     p.scale = g * g * 0.5 / 3.14159265358979323846;
     p.sym = (mirror_grid && nx == ny && nx >= 2 && N >= 2) ? 1 : 0;
+    p.sym_want_first = h->unit_first;
+    p.sym_want_count = h->unit_count;
+    if (h->unit_count >= 0 && !p.sym)
+        return fail(BQ_ERR_UNSUPPORTED, "a unit range needs a mirror-symmetric grid (bq_set_grid_symmetry / bq_grid_is_mirror)");
     p.ctr = h->ctr + 2 * h->ctr_next;
     h->ctr_next = (h->ctr_next + 1) % kCtrSlots;
     cudaEvent_t pa = nullptr, pb = nullptr;
@@ -250,6 +255,10 @@ int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t 
     if (h->profile) {
         cudaEventRecord(pb, st);
         h->prof_events.emplace_back(pa, pb);
+    }
+    if (e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        return fail(BQ_ERR_UNSUPPORTED, "no symmetric-grid kernel for this cutoff / grid: shard by row slab instead");
     }
     if (e != cudaSuccess) return fail_cuda(e, "launch_wigner");
     return BQ_OK;
@@ -875,6 +884,22 @@ int bq_set_grid_symmetry(bq_handle_t h, int mode)
     std::lock_guard<std::mutex> lk(h->mu);
     h->grid_mode = mode;
     return BQ_OK;
+}
+
+int bq_set_unit_range(bq_handle_t h, int64_t first, int64_t count)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (count >= 0 && first < 0) return fail(BQ_ERR_INVALID, "negative first unit");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->unit_first = count >= 0 ? first : 0;
+    h->unit_count = count >= 0 ? count : -1;
+    return BQ_OK;
+}
+
+int64_t bq_grid_units(int nx)
+{
+    const int64_t U = ((int64_t)nx + 1) / 2;
+    return nx >= 2 ? U * (U + 1) / 2 : 0;
 }
 
 int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny)

@@ -40,7 +40,9 @@ struct WigParams {
     unsigned int *ctr;  // [0] next tile, [1] CTAs that left
     // mirror-symmetric grids (wigner_sym_* kernels): U = ceil(S/2) mirror classes, U(U+1)/2 units per frame
     int sym, sym_U;
-    int64_t sym_units;
+    int64_t sym_units;  // units this launch evaluates per frame ...
+    int64_t sym_first;  // ... starting at this unit (a rank's share of one large grid; 0 = the whole grid)
+    int64_t sym_want_first, sym_want_count;  // caller's unit range (count < 0: all)
 };
 
 struct TraceMap {

@@ -523,11 +523,17 @@ __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__
     const double4 *tp = td + 2;
     const int m = K - 2;
     int r = 0;
-    for (; r + 1 < m; r += 2) {
+    // four steps per trip: with 5 CL DFMAs per step the loop control and the load latency of a two-step body
+    // showed as `wait` stalls (fp64 pipe 72 % busy at N = 256)
+#pragma unroll 1
+    for (; r + 3 < m; r += 4) {
         sym_step<CL>(s, cp[r], tp[r]);
         sym_step<CL>(s, cp[r + 1], tp[r + 1]);
+        sym_step<CL>(s, cp[r + 2], tp[r + 2]);
+        sym_step<CL>(s, cp[r + 3], tp[r + 3]);
     }
-    if (r < m) sym_step<CL>(s, cp[r], tp[r]);
+#pragma unroll 1
+    for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
     sym_tail<CL>(s, tp[m]);
 }
 
@@ -549,7 +555,7 @@ __device__ __forceinline__ void sym_load(const WigParams &p, int64_t chunk, SymP
 {
 #pragma unroll
     for (int c = 0; c < CL; ++c) {
-        const int64_t t = min(chunk * CL + c, p.sym_units - 1);
+        const int64_t t = p.sym_first + min(chunk * CL + c, p.sym_units - 1);
         sym_unit(t, p.sym_U, ua[c], ub[c]);
         s.al[c] = p.g * __ldg(p.xvec + ua[c]);
         s.be[c] = p.g * __ldg(p.xvec + ub[c]);
@@ -966,6 +972,13 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         // mirror-symmetric grid (the caller checked it): one recurrence per pair of grid lines
         p.sym_U = (p.nx + 1) / 2;
         p.sym_units = (int64_t)p.sym_U * (p.sym_U + 1) / 2;
+        p.sym_first = 0;
+        if (p.sym_want_count >= 0) {  // a share of the grid's units (multi-GPU sharding of one large grid)
+            if (p.sym_want_first < 0 || p.sym_want_first + p.sym_want_count > p.sym_units) return cudaErrorInvalidValue;
+            p.sym_first = p.sym_want_first;
+            p.sym_units = p.sym_want_count;
+            if (p.sym_units == 0) return cudaSuccess;
+        }
         const int64_t units = p.sym_units * p.batch;
         // Variants differ in units per thread (CL) and warps per SM.  The work is known exactly, so the choice is
         // by predicted duration: rounds of resident CTAs x units per thread / how well the variant keeps the fp64
@@ -978,15 +991,15 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         };
         static const SymVariant resident_variants[] = {
             {(const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 3, 128, 1.00},
-            {(const void *)wigner_sym_resident_kernel<2, 192, 2>, 12, 2, 192, 0.97},
-            {(const void *)wigner_sym_resident_kernel<2, 128, 2>, 11, 2, 128, 0.92},
+            {(const void *)wigner_sym_resident_kernel<2, 192, 2>, 12, 2, 192, 0.92},
+            {(const void *)wigner_sym_resident_kernel<2, 128, 2>, 11, 2, 128, 0.97},
             {(const void *)wigner_sym_resident_kernel<1, 256, 2>, 13, 1, 256, 0.80},
             {(const void *)wigner_sym_resident_kernel<1, 128, 4>, 9, 1, 128, 0.75},
         };
         static const SymVariant ring_variants[] = {
             {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
-            {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 0.97},
-            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.90},
+            {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 0.94},
+            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.96},
         };
         const bool resident = p.N <= kResidentMaxN;
         const size_t smem = resident ? (size_t)p.R_tot * 48 + 64 : (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
@@ -994,7 +1007,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         const int nvars = resident ? 5 : 3;
         const SymVariant *best = nullptr;
         double best_cost = 0.0;
-        if (smem <= dev.smem_optin && (resident || units >= 2LL * 256 * (dev.sm_count / 2))) {
+        if (smem <= dev.smem_optin && (resident || p.sym_want_count >= 0 || units >= 2LL * 256 * (dev.sm_count / 2))) {
             for (int i = 0; i < nvars; ++i) {
                 const SymVariant &v = vars[i];
                 if (dev.sym_force >= 0 && v.variant != dev.sym_force) continue;
@@ -1008,7 +1021,9 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 const int64_t ctas = (int64_t)occ * dev.sm_count;
                 const int64_t rounds = (tiles + ctas - 1) / ctas;
                 // a last round that fills only part of the machine still costs a whole tile
-                const double cost = (double)rounds * v.cl * v.threads * occ / v.eff;
+                // (the 2-unit tile loses ~6 % to the 3-unit one at cutoff 64 and wins ~5 % at cutoff <= 32)
+                const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93 : v.eff;
+                const double cost = (double)rounds * v.cl * v.threads * occ / eff;
                 if (!best || cost < best_cost) {
                     best = &v;
                     best_cost = cost;
@@ -1018,6 +1033,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         if (best)
             return run(best->plain, best->variant, best->threads, smem, p, best->cl, dev, st, launches,
                        (p.sym_units + best->cl - 1) / best->cl);
+        if (p.sym_want_count >= 0) return cudaErrorNotSupported;  // a unit range only means something to these kernels
         p.sym = 0;  // too few units (or too large a cutoff) for the ring kernel: point-by-point kernels below
     }
     if (p.N <= kResidentMaxN) {

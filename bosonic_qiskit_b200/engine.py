@@ -305,8 +305,17 @@ class Engine:
         if t.dtype != dtype or not t.is_contiguous():
             raise ValueError(f"{name} must be contiguous {dtype}")
 
-    def wigner_t(self, rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", out=None, stream=None):
-        """Device-resident Wigner: rho (batch, N, N) complex128 CUDA tensor -> (batch, ny, nx) float64 tensor."""
+    def grid_units(self, S: int) -> int:
+        """Units (pairs of grid lines, 8 points each) of an S x S mirror-symmetric grid."""
+        return int(self._lib.bq_grid_units(int(S)))
+
+    def wigner_t(self, rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", out=None, stream=None,
+                 unit_range=None):
+        """Device-resident Wigner: rho (batch, N, N) complex128 CUDA tensor -> (batch, ny, nx) float64 tensor.
+
+        ``unit_range=(first, count)``: evaluate only that share of a mirror-symmetric grid's units (multi-GPU sharding
+        of one large grid); the other points of ``out`` are left untouched.  Raises ``BQError`` (``BQ_ERR_UNSUPPORTED``)
+        when the grid or cutoff cannot use the symmetric-grid kernels."""
         import torch
 
         code = method_code(method)
@@ -323,10 +332,16 @@ class Engine:
             self._check_tensor(out, torch.float64, "out")
         with self._grid_lock:
             check(self._lib.bq_set_grid_symmetry(self._h, self._device_grid_mode(xvec, yvec)))
-            check(self._lib.bq_wigner_dev(self._h, ctypes.c_void_p(rho3.data_ptr()), N, N, N * N, batch,
-                                          ctypes.c_void_p(xvec.data_ptr()), xvec.numel(),
-                                          ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g), code,
-                                          ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+            if unit_range is not None:
+                check(self._lib.bq_set_unit_range(self._h, int(unit_range[0]), int(unit_range[1])))
+            try:
+                check(self._lib.bq_wigner_dev(self._h, ctypes.c_void_p(rho3.data_ptr()), N, N, N * N, batch,
+                                              ctypes.c_void_p(xvec.data_ptr()), xvec.numel(),
+                                              ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g), code,
+                                              ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+            finally:
+                if unit_range is not None:
+                    check(self._lib.bq_set_unit_range(self._h, 0, -1))
         return out[0] if single else out
 
     def partial_trace_sv_t(self, psi, traced: Sequence[int], out=None, stream=None):

@@ -117,9 +117,11 @@ def frames_to_wigner_sharded(psi, traced: Sequence[int], xvec, g: float = math.s
 
 def wigner_row_slabs(rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", engine=None, group=None,
                      dst: int = 0, gather: str | None = "nccl"):
-    """One large grid sharded by row slab (config c5): rank r evaluates rows ``[lo, hi)`` of ``yvec``
-    for every column; every rank needs the full ``rho``.  Same return convention as above with the
-    first dimension being grid rows."""
+    """One large grid on several GPUs (config c5).  Mirror-symmetric grids (what the reference builds) are shared out
+    by UNIT: every rank evaluates an equal range of the grid's pairs of grid lines with the symmetric-grid kernels
+    and one reduce assembles the grid on ``dst`` (``_shared_units_reduce``).  Any other grid is sharded by row slab:
+    rank r evaluates rows ``[lo, hi)`` of ``yvec`` for every column and the slabs are gathered.  Every rank needs
+    the full ``rho``.  Same return convention as above with the first dimension being grid rows."""
     import torch
 
     from .engine import get_engine
@@ -136,6 +138,10 @@ def wigner_row_slabs(rho, xvec, yvec=None, g: float = math.sqrt(2), method: str 
         dev = torch.device("cuda", eng.device)
         rho_t = torch.as_tensor(np.ascontiguousarray(rho, dtype=np.complex128), device=dev)
         x_t = torch.as_tensor(xvec, device=dev)
+        if world > 1 and gather is not None and (yvec is xvec or (len(yvec) == len(xvec) and np.array_equal(yvec, xvec))):
+            shared = _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, group)
+            if shared is not None:
+                return shared, (lo, hi)
         y_t = torch.as_tensor(np.ascontiguousarray(yvec[lo:hi]), device=dev)
         W_local = (eng.wigner_t(rho_t, x_t, y_t, g=g, method=method) if hi > lo
                    else torch.empty((0, len(xvec)), dtype=torch.float64, device=dev))
@@ -145,6 +151,36 @@ def wigner_row_slabs(rho, xvec, yvec=None, g: float = math.sqrt(2), method: str 
     if gather is None:
         return W_local, (lo, hi)
     return _gather_blocks(W_local, sizes, dst, group), (lo, hi)
+
+
+def _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, group):
+    """One mirror-symmetric grid on several GPUs: every rank evaluates an equal share of the grid's units (pairs of
+    grid lines, one Clenshaw recurrence for 8 points) into a zeroed full-size frame; the shares touch disjoint
+    points, so one reduce (sum) to ``dst`` assembles the grid exactly.  Returns None when this grid / cutoff /
+    engine cannot take that path (the caller then shards by row slab).  Collective: every rank decides alike."""
+    import torch
+
+    from ._lib import BQ_ERR_UNSUPPORTED, BQError
+
+    if world < 2 or not getattr(eng, "_grid_sharing", False) or not eng.grid_is_mirror(xvec):
+        return None
+    S = len(xvec)
+    total = eng.grid_units(S)
+    first, last = shard_range(total, rank, world)
+    W = torch.zeros((S, S), dtype=torch.float64, device=rho_t.device)
+    ok = 1
+    try:
+        eng.wigner_t(rho_t, x_t, g=g, method=method, out=W.unsqueeze(0), unit_range=(first, last - first))
+    except BQError as exc:
+        if exc.code != BQ_ERR_UNSUPPORTED:
+            raise
+        ok = 0
+    flag = torch.tensor([ok], device=rho_t.device)
+    _dist().all_reduce(flag, op=_dist().ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        return None
+    _dist().reduce(W, dst=dst, op=_dist().ReduceOp.SUM, group=group)
+    return W if rank == dst else None
 
 
 # ------------------------------------------------------------------------------------------------

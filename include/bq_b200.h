@@ -157,6 +157,14 @@ int bq_profile_read(bq_handle_t h, double *total_ms, int *launches);
  * caller vouches that the grids passed to `_dev` entry points are mirror-symmetric with yvec == xvec
  * until the mode is changed (the Python binding tests device grids once and caches the verdict).      */
 int bq_set_grid_symmetry(bq_handle_t h, int mode);
+/* One large mirror-symmetric grid shared by several GPUs (BASELINE config 5): the grid's bq_grid_units(nx)
+ * units (pairs of grid lines, 8 points each) all cost the same, so each rank takes a contiguous range of
+ * them: the next Wigner calls on this handle evaluate units [first, first + count) only and leave every other
+ * point of W untouched (zero the buffer first; the ranks' results then add up exactly, one reduce replaces
+ * the gather).  count < 0 restores the whole grid.  A call that cannot use the symmetric-grid kernels while a
+ * range is set fails with BQ_ERR_UNSUPPORTED (shard by row slab instead).                               */
+int bq_set_unit_range(bq_handle_t h, int64_t first, int64_t count);
+int64_t bq_grid_units(int nx);
 /* 1 if nx == ny >= 2, yvec[i] == xvec[i] and |xvec[i] + xvec[nx-1-i]| <= 4 ulp of max|xvec|; else 0 */
 int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny);
 

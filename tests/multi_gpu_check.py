@@ -57,6 +57,20 @@ def main():
         err = np.abs(full_local[1] - ref).max() / np.abs(ref).max()
         print(f"[oracle] frame 1 max|dW|/max|W| = {err:.2e}", flush=True)
         ok &= err < 1e-10
+    # one mirror-symmetric grid shared out by unit range + reduce (the symmetric-grid kernels)
+    for Nc, Sc in ((32, 200), (100, 420)):
+        rho2 = workloads.random_rho(Nc, seed=7, rank=3)
+        x2 = np.linspace(-6, 6, Sc)
+        full2 = np.array(eng.wigner(rho2, x2))
+        Wu, _ = wigner_row_slabs(rho2, x2, engine=eng)
+        if rank == 0:
+            got = Wu.cpu().numpy()
+            same = np.array_equal(got, full2)
+            print(f"[shared units N={Nc} S={Sc}] reduced {got.shape}, bit-identical to single-GPU result: {same}, "
+                  f"max diff {np.abs(got - full2).max():.2e}", flush=True)
+            ok &= same
+        dist.barrier()
+
     flag = torch.tensor([1 if ok else 0], device=torch.device("cuda", local))
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
