@@ -135,12 +135,12 @@ def wigner_row_slabs(rho, xvec, yvec=None, g: float = math.sqrt(2), method: str 
     sizes = shard_sizes(ny, world)
     on_gpu = hasattr(eng, "wigner_t") and getattr(eng, "device", None) is not None
     if on_gpu:
-        dev = torch.device("cuda", eng.device)
+        dev = getattr(eng, "torch_device", None) or torch.device("cuda", eng.device)
         rho_t = torch.as_tensor(np.ascontiguousarray(rho, dtype=np.complex128), device=dev)
         x_t = torch.as_tensor(xvec, device=dev)
         if world > 1 and gather is not None and (yvec is xvec or (len(yvec) == len(xvec) and np.array_equal(yvec, xvec))):
-            shared = _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, group)
-            if shared is not None:
+            taken, shared = _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, group)
+            if taken:  # (``shared`` is None on every rank but ``dst``)
                 return shared, (lo, hi)
         y_t = torch.as_tensor(np.ascontiguousarray(yvec[lo:hi]), device=dev)
         W_local = (eng.wigner_t(rho_t, x_t, y_t, g=g, method=method) if hi > lo
@@ -156,14 +156,15 @@ def wigner_row_slabs(rho, xvec, yvec=None, g: float = math.sqrt(2), method: str 
 def _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, group):
     """One mirror-symmetric grid on several GPUs: every rank evaluates an equal share of the grid's units (pairs of
     grid lines, one Clenshaw recurrence for 8 points) into a zeroed full-size frame; the shares touch disjoint
-    points, so one reduce (sum) to ``dst`` assembles the grid exactly.  Returns None when this grid / cutoff /
-    engine cannot take that path (the caller then shards by row slab).  Collective: every rank decides alike."""
+    points, so one reduce (sum) to ``dst`` assembles the grid exactly.  Returns ``(taken, W)``: ``taken`` is False
+    when this grid / cutoff / engine cannot take that path (the caller then shards by row slab) and every rank
+    decides alike; ``W`` is the grid on ``dst`` and None elsewhere."""
     import torch
 
     from ._lib import BQ_ERR_UNSUPPORTED, BQError
 
     if world < 2 or not getattr(eng, "_grid_sharing", False) or not eng.grid_is_mirror(xvec):
-        return None
+        return False, None
     S = len(xvec)
     total = eng.grid_units(S)
     first, last = shard_range(total, rank, world)
@@ -178,9 +179,9 @@ def _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, gro
     flag = torch.tensor([ok], device=rho_t.device)
     _dist().all_reduce(flag, op=_dist().ReduceOp.MIN, group=group)
     if int(flag.item()) == 0:
-        return None
+        return False, None
     _dist().reduce(W, dst=dst, op=_dist().ReduceOp.SUM, group=group)
-    return W if rank == dst else None
+    return True, (W if rank == dst else None)
 
 
 # ------------------------------------------------------------------------------------------------
