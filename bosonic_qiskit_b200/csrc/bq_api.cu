@@ -425,6 +425,7 @@ int bq_create(bq_handle_t *out, int device)
         h->dev.pts8 = (p8 && p8[0] == '0') ? 0 : 1;  // default on: measured 87.6 % vs 82.7 % of fp64 peak at N=64
         const char *sv = std::getenv("BQ_B200_SYM_VARIANT");
         h->dev.sym_force = sv ? std::atoi(sv) : -1;
+        if (const char *sp = std::getenv("BQ_B200_SYM_SPLIT")) std::sscanf(sp, "%d:%d", &h->dev.sym_split_main, &h->dev.sym_split_tail);
         const char *env = std::getenv("BQ_B200_SASS");
         h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
     }

@@ -8,7 +8,7 @@ namespace bq {
 
 constexpr int kResidentMaxN = 64;  // stream fits twice per SM in shared memory up to this cutoff
 constexpr int kMaxQubits = 40;
-constexpr int kKernelSlots = 32;
+constexpr int kKernelSlots = 40;
 
 // records in the coefficient stream of cutoff N, and the first record of the diagonal with K = N-L
 // coefficients (K >= 2); layout described in bq_common.cuh
@@ -22,6 +22,7 @@ struct DeviceInfo {
     // per-kernel launch cache (attribute set once, occupancy looked up once per shared-memory size)
     int pts8 = 0;       // use the 8-points-per-thread resident kernel for large grids
     int sym_force = -1; // >= 0: tuning aid (env BQ_B200_SYM_VARIANT), only this symmetric-kernel variant is eligible
+    int sym_split_main = -1, sym_split_tail = -1;  // tuning aid (env BQ_B200_SYM_SPLIT=main:tail): whole rounds / remainder
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     bool configured[kKernelSlots] = {};
     int occ[kKernelSlots] = {};

@@ -855,7 +855,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 16;
+constexpr int kVariants = 19;
 constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
@@ -875,6 +875,9 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq26wigner_sym_resident_kernelILi1ELi256ELi2EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_sym_diag_kernelILi2ELi256ELi3EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_sym_diag_kernelILi2ELi384ELi3EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_sym_diag_kernelILi1ELi256ELi3EEEvNS_9WigParamsE",
+    "_ZN2bq26wigner_sym_resident_kernelILi4ELi256ELi1EEEvNS_9WigParamsE",
+    "_ZN2bq22wigner_sym_diag_kernelILi4ELi256ELi3EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -983,7 +986,8 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         // Variants differ in units per thread (CL) and warps per SM.  The work is known exactly, so the choice is
         // by predicted duration: rounds of resident CTAs x units per thread / how well the variant keeps the fp64
         // pipe busy (measured, tools/roofline_sweep.py --sharing on).  A 1024 x 1024 grid has 131 328 units = 1.16
-        // rounds of the 3-unit tile on 296 CTAs but 1.73 rounds of the 2-unit tile: the latter finishes first.
+        // rounds of the 3-unit tile on 296 CTAs, 1.73 rounds of the 2-unit tile and 0.87 rounds of the 4-unit tile on
+        // 148 CTAs: the last finishes first (0.144 ms against 0.157 and 0.168) although its loop is the least efficient.
         struct SymVariant {
             const void *plain;
             int variant, cl, threads;
@@ -995,44 +999,86 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_resident_kernel<2, 128, 2>, 11, 2, 128, 0.97},
             {(const void *)wigner_sym_resident_kernel<1, 256, 2>, 13, 1, 256, 0.80},
             {(const void *)wigner_sym_resident_kernel<1, 128, 4>, 9, 1, 128, 0.75},
+            {(const void *)wigner_sym_resident_kernel<4, 256, 1>, 17, 4, 256, 0.92},  // one CTA per SM: 1024 units per round
         };
         static const SymVariant ring_variants[] = {
             {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
             {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 0.94},
             {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.96},
+            {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 16, 1, 256, 0.60},
+            {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 18, 4, 256, 0.90},
         };
         const bool resident = p.N <= kResidentMaxN;
         const size_t smem = resident ? (size_t)p.R_tot * 48 + 64 : (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
         const SymVariant *vars = resident ? resident_variants : ring_variants;
-        const int nvars = resident ? 5 : 3;
-        const SymVariant *best = nullptr;
-        double best_cost = 0.0;
+        const int nvars = resident ? 6 : 5;
+        struct Cand {
+            const SymVariant *v;
+            int occ;
+            int64_t ctas, tiles;
+            double round_cost;  // one round of resident CTAs: units per SM / how busy the variant keeps the fp64 pipe
+        };
+        Cand cand[6];
+        int ncand = 0;
         if (smem <= dev.smem_optin && (resident || p.sym_want_count >= 0 || units >= 2LL * 256 * (dev.sm_count / 2))) {
             for (int i = 0; i < nvars; ++i) {
                 const SymVariant &v = vars[i];
-                if (dev.sym_force >= 0 && v.variant != dev.sym_force) continue;
                 const void *func = nullptr;
                 int occ = 0;
                 if (occupancy(v.plain, v.variant, v.threads, smem, dev, &func, &occ) != cudaSuccess) {
                     cudaGetLastError();
                     continue;
                 }
-                const int64_t tiles = (((p.sym_units + v.cl - 1) / v.cl + v.threads - 1) / v.threads) * p.batch;
-                const int64_t ctas = (int64_t)occ * dev.sm_count;
-                const int64_t rounds = (tiles + ctas - 1) / ctas;
-                // a last round that fills only part of the machine still costs a whole tile
                 // (the 2-unit tile loses ~6 % to the 3-unit one at cutoff 64 and wins ~5 % at cutoff <= 32)
                 const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93 : v.eff;
-                const double cost = (double)rounds * v.cl * v.threads * occ / eff;
-                if (!best || cost < best_cost) {
-                    best = &v;
-                    best_cost = cost;
-                }
+                Cand &c = cand[ncand++];
+                c.v = &v;
+                c.occ = occ;
+                c.ctas = (int64_t)occ * dev.sm_count;
+                c.tiles = (((p.sym_units + v.cl - 1) / v.cl + v.threads - 1) / v.threads) * p.batch;
+                c.round_cost = (double)v.cl * v.threads * occ / eff;
             }
         }
-        if (best)
-            return run(best->plain, best->variant, best->threads, smem, p, best->cl, dev, st, launches,
-                       (p.sym_units + best->cl - 1) / best->cl);
+        auto launch_range = [&](const SymVariant &v, int64_t first, int64_t count) {
+            WigParams q = p;
+            q.sym_first = first;
+            q.sym_units = count;
+            return run(v.plain, v.variant, v.threads, smem, q, v.cl, dev, st, launches, (count + v.cl - 1) / v.cl);
+        };
+        // A last round that fills only part of the machine still costs a whole tile.  Tried and measured (tools/
+        // sym_split_sweep.py, profiles/r1d_sym_split.txt): whole rounds in one launch and the remainder in a SECOND
+        // launch of a 1-unit variant.  No gain -- a tile's duration is ~46 us of latency + ~17.5 us per unit per thread
+        // at cutoff 64, so the 1-unit remainder costs 2/3 of a 3-unit round.  The split stays as a tuning aid
+        // (BQ_B200_SYM_SPLIT=main:tail); what helps a 1024 x 1024 grid is the 4-unit tile, which covers it in ONE round.
+        const Cand *best = nullptr, *split_main = nullptr, *split_tail = nullptr;
+        double best_cost = 0.0;
+        int64_t split_tpf = 0;
+        for (int i = 0; i < ncand; ++i) {
+            const Cand &c = cand[i];
+            if (dev.sym_force >= 0 && c.v->variant != dev.sym_force) continue;
+            const double cost = (double)((c.tiles + c.ctas - 1) / c.ctas) * c.round_cost;
+            if (!best || cost < best_cost) {
+                best = &c;
+                best_cost = cost;
+            }
+        }
+        if (dev.sym_split_main >= 0) {  // tuning aid: BQ_B200_SYM_SPLIT=main:tail
+            for (int i = 0; i < ncand; ++i) {
+                if (cand[i].v->variant == dev.sym_split_main) split_main = &cand[i];
+                if (cand[i].v->variant == dev.sym_split_tail) split_tail = &cand[i];
+            }
+            if (split_main && split_tail) {
+                const int64_t rounds = split_main->tiles / split_main->ctas;
+                split_tpf = rounds * split_main->ctas / p.batch;
+            }
+        }
+        if (split_main && split_tail && split_tpf > 0) {
+            const int64_t m = std::min<int64_t>(split_tpf * split_main->v->threads * split_main->v->cl, p.sym_units);
+            cudaError_t e = launch_range(*split_main->v, p.sym_first, m);
+            if (e != cudaSuccess || m == p.sym_units) return e;
+            return launch_range(*split_tail->v, p.sym_first + m, p.sym_units - m);
+        }
+        if (best) return launch_range(*best->v, p.sym_first, p.sym_units);
         if (p.sym_want_count >= 0) return cudaErrorNotSupported;  // a unit range only means something to these kernels
         p.sym = 0;  // too few units (or too large a cutoff) for the ring kernel: point-by-point kernels below
     }
