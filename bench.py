@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--frames", type=int, default=None, help="frames per rank (c3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="auto", choices=["auto", "frames", "grid"],
+                    help="N > 1: 'frames' = every GPU its own frames (weak scaling); 'grid' = ONE grid shared out by unit "
+                         "range + one reduce (strong scaling; what BASELINE config 5 names). auto: grid for c5, else frames")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"],
                     help="N>1: how finished grids reach rank 0 (peer = kernels store into rank 0's buffer over NVLink)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -245,7 +248,7 @@ def run_reference(args, rank: int, world: int):
     sample = f"{rows} of {S} grid rows x {S} columns per step, {procs} worker processes (rows split evenly)"
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if one_grid else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -307,6 +310,18 @@ def main():
     multi_sets = "traced_sets" in wl
     frames = cfg["frames_per_gpu"]
     points_rank = frames * S * S
+    # one grid on all GPUs (BASELINE config 5): every rank evaluates an equal range of the grid's units, one reduce
+    one_grid = world > 1 and not multi_sets and frames == 1 and (args.sharding == "grid" or (args.sharding == "auto" and args.config == "c5"))
+    if one_grid:
+        if not eng.grid_is_mirror(x_np):
+            raise SystemExit("--sharding grid needs the mirror-symmetric grid the reference builds")
+        from bosonic_qiskit_b200.parallel import shard_range
+
+        u_first, u_last = shard_range(eng.grid_units(S), rank, world)
+        cfg.update({"frames_per_gpu": 1.0 / world, "global_frames": 1,
+                    "sharding": "one grid: equal ranges of its units (pairs of grid lines, 8 points each) per GPU, then one NCCL reduce to rank 0"})
+    points_global = points_rank if one_grid else points_rank * world
+    points_launch = points_rank / world if one_grid else points_rank
 
     psi_t = torch.from_numpy(wl["psi"]).to(dev)
     x_t = torch.from_numpy(x_np).to(dev)
@@ -314,7 +329,7 @@ def main():
     rho_t = torch.empty((frames, N, N), dtype=torch.complex128, device=dev)
     gathered = None
     peer = None
-    gather_mode = args.gather if (world > 1 and not multi_sets) else ("nccl" if world > 1 and args.gather != "none" else "none")
+    gather_mode = "reduce" if one_grid else args.gather if (world > 1 and not multi_sets) else ("nccl" if world > 1 and args.gather != "none" else "none")
     if world > 1 and gather_mode == "nccl":
         gathered = torch.empty((world * frames, S, S), dtype=torch.float64, device=dev) if rank == 0 else None
     if world > 1 and gather_mode == "peer":
@@ -337,6 +352,11 @@ def main():
                                                          len(sets[0]), len(sets), ctypes.c_void_p(rho_t.data_ptr()),
                                                          ctypes.c_void_p(stream.cuda_stream)))
             eng.wigner_t(rho_t, x_t, out=W_t)
+        elif one_grid:
+            eng.partial_trace_sv_t(psi_t, wl["traced"], out=rho_t)  # 16 KiB of psi: replicated on every rank
+            W_t.zero_()
+            eng.wigner_t(rho_t, x_t, out=W_t, unit_range=(u_first, u_last - u_first))
+            dist.reduce(W_t, dst=0, op=dist.ReduceOp.SUM)  # the shares touch disjoint points: the sum assembles the grid
         elif peer is not None:
             # fused compute + gather: the kernel's stores land in rank 0's buffer (NVLink peer memory)
             eng.state_to_wigner_t(psi_t, wl["traced"], x_t, out=peer_out, rho_out=rho_t)
@@ -382,7 +402,7 @@ def main():
         total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = total_ms / args.steps
-    value = points_rank * world / (ms_per_step * 1e-3)
+    value = points_global / (ms_per_step * 1e-3)
 
     # ---- the same step with recurrence sharing off: the point-by-point kernels (the plain fp64-roofline case) ------
     pbp = None
@@ -415,7 +435,33 @@ def main():
     # ---- accuracy of what was just timed (rank 0, a row sample) ---------------------------------
     # ---- end-to-end through the public NumPy API (host buffers) ---------------------------------
     e2e = None
-    if not multi_sets:
+    if one_grid:
+        from bosonic_qiskit_b200.parallel import wigner_row_slabs
+
+        psi_pin = eng.pinned_empty(wl["psi"].shape, np.complex128)
+        psi_pin[...] = wl["psi"]
+        out_pin = torch.empty((S, S), dtype=torch.float64, pin_memory=True) if rank == 0 else None
+
+        def step_host():
+            rho_h = eng.partial_trace_sv(psi_pin[0], wl["traced"])
+            Wg, _ = wigner_row_slabs(rho_h, x_np, engine=eng)
+            if rank == 0:
+                out_pin.copy_(Wg)  # device -> pinned host (synchronous)
+            dist.barrier()
+
+        step_host()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": points_global * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(psi_pin.nbytes + world * N * N * 16), "d2h_bytes_per_step": int(S * S * 8 + N * N * 16),
+               "ms_per_step": 1e3 * dt / args.steps,
+               "api": "Engine.partial_trace_sv + parallel.wigner_row_slabs (rho to every GPU, unit ranges, reduce) + copy to host on rank 0"}
+    elif not multi_sets:
         psi_pin = eng.pinned_empty(wl["psi"].shape, np.complex128)
         psi_pin[...] = wl["psi"]
         out_pin = eng.pinned_empty((frames, S, S), np.float64)
@@ -474,7 +520,7 @@ def main():
         pass
     F = workloads.flops_per_point(N)
     kern_avg_ms = kern_ms / max(kern_n, 1)
-    achieved_tf = points_rank * F / (kern_avg_ms * 1e-3) / 1e12
+    achieved_tf = points_launch * F / (kern_avg_ms * 1e-3) / 1e12
     big = points_rank >= 148 * 2048
     if shared_used:
         kname = "wigner_sym_resident_kernel" if N <= 64 else ("wigner_sym_diag_kernel" if big else "wigner_stream_kernel")
@@ -485,18 +531,18 @@ def main():
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
         "peak_source": "DFMA probe kernel run for 1 s on this GPU immediately before the timed region (bq_fp64_peak); "
                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
-        "flops_per_point": F, "points_per_launch": points_rank, "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
+        "flops_per_point": F, "points_per_launch": points_launch, "kernel_ms": kern_avg_ms, "kernel_launches_timed": kern_n,
         "kernel_share_of_step": kern_avg_ms / ms_per_step,
         "traffic": traffic,
-        "hbm_store": {"bound": "hbm", "achieved": points_rank * 8 / (kern_avg_ms * 1e-3) / 1e9, "peak": hbm_peak,
+        "hbm_store": {"bound": "hbm", "achieved": points_launch * 8 / (kern_avg_ms * 1e-3) / 1e9, "peak": hbm_peak,
                       "unit": "GB/s", "peak_source": hbm_src,
-                      "frac": points_rank * 8 / (kern_avg_ms * 1e-3) / 1e9 / hbm_peak},
+                      "frac": points_launch * 8 / (kern_avg_ms * 1e-3) / 1e9 / hbm_peak},
     }
     if shared_used:
         # `achieved` above is the ALGORITHMIC work of the reference's point-by-point recurrence over the
         # kernel's time: it exceeds the fp64 peak because the kernel shares one recurrence between 8 grid points.
         # What the fp64 pipe actually executed, and the point-by-point kernels timed in the same run, are next to it.
-        units = frames * workloads.shared_units(S)
+        units = (u_last - u_first) if one_grid else frames * workloads.shared_units(S)
         ex_tf = units * workloads.flops_per_unit_shared(N) / (kern_avg_ms * 1e-3) / 1e12
         roofline["note"] = ("frac > 1: algorithmic flops of the reference recurrence (one per grid point) / kernel time; the "
                             "symmetric-grid kernel runs one recurrence per pair of grid lines. executed = flops it really "
@@ -525,13 +571,21 @@ def main():
                   "max_abs_drho_over_max_rho": float(np.abs(rho_dev - rho_ref).max() / np.abs(rho_ref).max()),
                   "tolerance": 1e-10}
 
+    if one_grid:
+        # the assembled grid against rows evaluated on this GPU alone by the point-by-point kernels
+        rows = torch.arange(0, S, max(S // 16, 1), device=dev)
+        W_rows = eng.wigner_t(rho_t[0], x_t, x_t[rows].contiguous())
+        parity = {"max_abs_dW_over_max_W_vs_rows_on_one_gpu": float((W_t[0][rows] - W_rows).abs().max().item() / W_t[0].abs().max().item()),
+                  "rows_checked": int(rows.numel()), "tolerance": 1e-10}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if one_grid else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": cfg, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "gather": None if world == 1 else {"peer": "kernel stores finished tiles into rank 0's buffer over NVLink (CUDA IPC peer memory), inside the step",
                                              "nccl": "torch.distributed.gather (NCCL) to rank 0 inside the step",
+                                             "reduce": "torch.distributed.reduce (NCCL, sum of disjoint shares) to rank 0 inside the step",
                                              "none": "none (results stay sharded)"}[gather_mode],
     }
     emit(out)

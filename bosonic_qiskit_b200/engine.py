@@ -72,7 +72,7 @@ class Engine:
         self._pool_lock = threading.Lock()
         self._grid_lock = threading.Lock()
         self._grid_sharing = True
-        self._grid_verdicts: dict[tuple, bool] = {}
+        self._grid_verdicts: dict[int, tuple] = {}
         self._stage = None  # local block for symmetric-grid results bound for a peer buffer
 
     def close(self) -> None:
@@ -121,17 +121,32 @@ class Engine:
 
     def _device_grid_mode(self, xvec, yvec) -> int:
         """Grid-symmetry mode for a ``_dev`` call: the library cannot read a device grid without a synchronisation,
-        so the binding tests each grid tensor once (keyed on storage, size and torch's version counter)."""
+        so the binding tests each grid TENSOR OBJECT once.  The verdict is tied to the object's lifetime (a weak
+        reference evicts it) and to torch's version counter -- never to the storage address, which the caching
+        allocator hands to the next tensor."""
         if not self._grid_sharing:
             return 0
-        key = (xvec.data_ptr(), xvec.numel(), xvec._version, yvec.data_ptr(), yvec.numel(), yvec._version)
-        verdict = self._grid_verdicts.get(key)
-        if verdict is None:
-            if len(self._grid_verdicts) > 64:
-                self._grid_verdicts.clear()
-            xh = xvec.detach().cpu().numpy()
-            yh = xh if yvec is xvec else yvec.detach().cpu().numpy()
-            verdict = self._grid_verdicts[key] = self.grid_is_mirror(xh, yh)
+        if yvec is not xvec and (yvec.data_ptr() != xvec.data_ptr() or yvec.numel() != xvec.numel()):
+            if yvec.numel() != xvec.numel():
+                return 1
+            key_obj, other = xvec, yvec
+        else:
+            key_obj, other = xvec, None
+        entry = self._grid_verdicts.get(id(key_obj))
+        stamp = (key_obj._version, None if other is None else (id(other), other._version))
+        if entry is not None and entry[0]() is key_obj and entry[1] == stamp and (other is None or entry[2]() is other):
+            return 2 if entry[3] else 1
+        xh = key_obj.detach().cpu().numpy()
+        yh = xh if other is None else other.detach().cpu().numpy()
+        verdict = self.grid_is_mirror(xh, yh)
+        verdicts, kid = self._grid_verdicts, id(key_obj)
+        if len(verdicts) > 256:
+            verdicts.clear()
+
+        def _evict(_ref, verdicts=verdicts, kid=kid):
+            verdicts.pop(kid, None)
+
+        verdicts[kid] = (weakref.ref(key_obj, _evict), stamp, None if other is None else weakref.ref(other), verdict)
         return 2 if verdict else 1
 
     def profile(self, on: bool) -> None:

@@ -155,3 +155,29 @@ def test_symmetry_of_the_result_is_exact(engine):
     x = np.linspace(-4, 4, 64)
     W = np.array(engine.wigner(rho, x))
     assert np.array_equal(W, W[::-1, :]) and np.array_equal(W, W[:, ::-1]) and np.array_equal(W, W.T)
+
+
+def test_grid_verdict_follows_the_tensor_not_its_address(engine):
+    """The device entry points test each grid tensor once.  The caching allocator hands a freed grid's address to the
+    next grid of the same size: a mirror verdict must not survive that (it would run the symmetric kernels on a
+    grid that is not mirror-symmetric)."""
+    import torch
+
+    dev = torch.device("cuda", engine.device)
+    rho = workloads.random_rho(12, seed=5)
+    rho_t = torch.from_numpy(rho).to(dev)
+    grids = [np.linspace(-5, 5, 64), np.linspace(-4, 5, 64), np.linspace(-5, 5, 64), np.linspace(-5, 4.5, 64)]
+    seen = set()
+    for x in grids:
+        x_t = torch.from_numpy(x).to(dev)
+        seen.add(x_t.data_ptr())
+        W = engine.wigner_t(rho_t, x_t).cpu().numpy()
+        assert rel_err(W, wigner_clenshaw(rho, x)) < TOL
+        del x_t
+    # in-place change of a grid that was judged mirror-symmetric
+    x_t = torch.from_numpy(grids[0]).to(dev)
+    engine.wigner_t(rho_t, x_t)
+    x_t.copy_(torch.from_numpy(grids[1]).to(dev))
+    W = engine.wigner_t(rho_t, x_t).cpu().numpy()
+    assert rel_err(W, wigner_clenshaw(rho, grids[1])) < TOL
+    assert len(seen) < len(grids)  # the allocator did recycle an address (otherwise this test shows nothing)
