@@ -40,6 +40,10 @@ SIGNATURES = {
                                c_double, c_int, c_void_p]),
     "bq_wigner_dev": (c_int, [_H, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p, c_int,
                               c_double, c_int, c_void_p, c_void_p]),
+    "bq_wigner_fft_host": (c_int, [_H, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int, c_double, c_void_p,
+                                   c_void_p]),
+    "bq_wigner_fft_dev": (c_int, [_H, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int, c_double, c_void_p,
+                                  c_void_p, c_void_p]),
     "bq_state_to_wigner_host": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,
                                         c_int, c_double, c_int, c_void_p, c_void_p]),
     "bq_state_to_wigner_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,

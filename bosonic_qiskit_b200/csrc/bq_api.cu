@@ -74,6 +74,7 @@ struct bq_handle_s {
     std::map<std::vector<int>, bq::TraceMap *> maps;        // (n_qubits, n_traced, sets...) -> device maps
     Buffer cs, partial, rho_tmp;                            // kernel scratch
     Buffer in_dev, out_dev, rho_dev, grid_dev, small_dev;   // staging for _host calls
+    Buffer fft_a, fft_m, fft_r, fft_t, fft_x;               // method="fft" scratch
     std::vector<double> grid_host;                          // what grid_dev currently holds
     bool grid_host_mirror = false;                          // ... and whether it is a mirror-symmetric square grid
     int64_t unit_first = 0, unit_count = -1;                // bq_set_unit_range (count < 0: whole grid)
@@ -451,7 +452,8 @@ int bq_destroy(bq_handle_t h)
         cudaDeviceSynchronize();
         for (auto &kv : h->tabs) cudaFree(kv.second);
         for (auto &kv : h->maps) cudaFree(kv.second);
-        Buffer *bufs[] = {&h->cs, &h->partial, &h->rho_tmp, &h->in_dev, &h->out_dev, &h->rho_dev, &h->grid_dev, &h->small_dev};
+        Buffer *bufs[] = {&h->cs, &h->partial, &h->rho_tmp, &h->in_dev, &h->out_dev, &h->rho_dev, &h->grid_dev, &h->small_dev,
+                          &h->fft_a, &h->fft_m, &h->fft_r, &h->fft_t, &h->fft_x};
         for (Buffer *b : bufs) b->release();
         for (auto &pr : h->prof_events) {
             cudaEventDestroy(pr.first);
@@ -728,6 +730,93 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
                      mirror);
     if (rc) return rc;
     if (!direct) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
+}
+
+// ---- method="fft" ------------------------------------------------------------------------------
+namespace {
+
+// p axis of qutip's _wigner_fft / _psi_wigner_fft, same operation order as the NumPy expressions:
+//   xs = xvec * g / sqrt(2);  p = arange(-n/4, n/4) * pi / (n * (xs[1] - xs[0]));  yvec = p * sqrt(2) / g
+int fft_axis(const double *xvec, int nx, double g, double *yvec_out, double *scale)
+{
+    const double n = 2.0 * nx;
+    const double dx = xvec[1] * g / std::sqrt(2.0) - xvec[0] * g / std::sqrt(2.0);
+    if (!(dx != 0.0) || !std::isfinite(dx)) return fail(BQ_ERR_INVALID, "method='fft' needs a uniformly spaced xvec with xvec[1] != xvec[0]");
+    auto p_at = [&](int c) { return (-n / 4.0 + c) * 3.14159265358979323846 / (n * dx); };
+    if (yvec_out)
+        for (int c = 0; c < nx; ++c) yvec_out[c] = p_at(c) * std::sqrt(2.0) / g;
+    *scale = (0.5 * g * g) / (p_at(1) - p_at(0)) / n;
+    return BQ_OK;
+}
+
+int wigner_fft_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                    const double *xvec, int nx, double g, double *d_W, double *yvec_out, cudaStream_t st)
+{
+    if (N < 1 || N > 16384) return fail(BQ_ERR_INVALID, "cutoff N out of range [1, 16384]");
+    if (batch < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (nx < 2) return fail(BQ_ERR_INVALID, "method='fft' needs at least two grid points (the p axis comes from xvec[1] - xvec[0])");
+    if (nx > 14000) return fail(BQ_ERR_UNSUPPORTED, "method='fft': grids above 14000 points per axis do not fit the band buffer");
+    if (ld < N) return fail(BQ_ERR_INVALID, "leading dimension smaller than N");
+    if (!std::isfinite(g) || g == 0.0) return fail(BQ_ERR_INVALID, "g must be finite and non-zero");
+    if (!xvec || (batch > 0 && (!d_rho || !d_W))) return fail(BQ_ERR_INVALID, "NULL pointer");
+    double scale = 0.0;
+    int rc = fft_axis(xvec, nx, g, yvec_out, &scale);
+    if (rc || batch == 0) return rc;
+    const size_t S = (size_t)nx;
+    CU(h->fft_x.reserve(S * sizeof(double)));
+    CU(h->fft_a.reserve((size_t)N * S * sizeof(double)));
+    CU(h->fft_m.reserve((size_t)N * S * sizeof(double2)));
+    CU(h->fft_r.reserve(S * S * sizeof(double2)));
+    CU(h->fft_t.reserve(2 * S * sizeof(double2)));
+    CU(cudaMemcpyAsync(h->fft_x.ptr, xvec, S * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));  // xvec is the caller's (possibly pageable) memory: do not return before it is read
+    for (int b = 0; b < batch; ++b) {
+        int nl = 0;
+        cudaError_t e = bq::launch_wigner_fft(d_rho + (int64_t)b * rho_stride, N, ld, (const double *)h->fft_x.ptr, nx, g, scale,
+                                              (double *)h->fft_a.ptr, (double2 *)h->fft_m.ptr, (double2 *)h->fft_r.ptr,
+                                              (double2 *)h->fft_t.ptr, d_W + (int64_t)b * nx * nx, st, &nl);
+        h->launches += nl;
+        if (e != cudaSuccess) return fail_cuda(e, "launch_wigner_fft");
+    }
+    return BQ_OK;
+}
+
+}  // namespace
+
+int bq_wigner_fft_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                      const double *xvec, int nx, double g, double *d_W_out, double *yvec_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = order_stream(h, st);
+    if (rc) return rc;
+    return wigner_fft_core(h, (const double2 *)d_rho, N, ld, rho_stride, batch, xvec, nx, g, d_W_out, yvec_out, st);
+}
+
+int bq_wigner_fft_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                       const double *xvec, int nx, double g, double *W_out, double *yvec_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (N < 1 || ld < N || batch < 0 || nx < 0) return fail(BQ_ERR_INVALID, "bad size");
+    if (batch > 0 && (!rho || !W_out)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    if (batch > 1 && rho_stride < 0) return fail(BQ_ERR_INVALID, "negative rho_stride");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    int rc = order_stream(h, h->stream);
+    if (rc) return rc;
+    const size_t in_elems = batch ? (size_t)((int64_t)(batch - 1) * rho_stride + (int64_t)(N - 1) * ld + N) : 0;
+    const size_t out_b = (size_t)batch * nx * nx * sizeof(double);
+    CU(h->in_dev.reserve(std::max<size_t>(in_elems, 1) * sizeof(double2)));
+    CU(h->out_dev.reserve(std::max<size_t>(out_b, 8)));
+    HostTimer timer(h);
+    if (in_elems) CU(cudaMemcpyAsync(h->in_dev.ptr, rho, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    rc = wigner_fft_core(h, (const double2 *)h->in_dev.ptr, N, ld, rho_stride, batch, xvec, nx, g, (double *)h->out_dev.ptr,
+                         yvec_out, h->stream);
+    if (rc) return rc;
+    if (out_b) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
     return timer.finish();
 }
 

@@ -58,6 +58,9 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
                             int64_t cs_stride, cudaStream_t st);
 cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches);
 bool patched_sass_available();
+// method="fft": scratch A [N][S] doubles, M [N][S], R [S][S], T [2S] complex; W is [S][S] (indexed [ip][ix])
+cudaError_t launch_wigner_fft(const double2 *rho, int N, int64_t ld, const double *d_xvec, int S, double g, double scale,
+                              double *A, double2 *M, double2 *R, double2 *T, double *W, cudaStream_t st, int *launches);
 
 // K1: rho[set][b] = Psi Psi^dagger.  `maps` is a device array of n_sets TraceMaps (same n_keep / n_trace);
 // rho_out is [n_sets][batch][D][D]; `partial` is scratch of at least trace_sv_scratch_bytes().

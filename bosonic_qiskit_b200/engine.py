@@ -260,6 +260,8 @@ class Engine:
     def wigner(self, rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", out=None) -> np.ndarray:
         """``rho``: (N, N) or (batch, N, N) -> W (ny, nx) or (batch, ny, nx), indexed [iy, ix]."""
         code = method_code(method)
+        if code == METHODS["fft"]:  # returns the tuple (W, yvec) on its own p axis, like qutip.wigner
+            return self.wigner_fft(rho, xvec, g=g)
         rho = _c128(rho)
         single = rho.ndim == 2
         rho3 = rho.reshape(1, *rho.shape) if single else rho
@@ -277,10 +279,52 @@ class Engine:
                                        len(yvec), float(g), code, _ptr(out)))
         return out[0] if single else out
 
+    def wigner_fft(self, rho, xvec, g: float = math.sqrt(2)):
+        """``qutip.wigner(..., method="fft")``: ``rho`` (N, N) or (batch, N, N) -> ``(W, yvec)`` with ``W[ip, ix]`` of
+        shape (S, S) or (batch, S, S) on the p axis ``yvec`` the method derives from the (uniform) x grid."""
+        rho = _c128(rho)
+        single = rho.ndim == 2
+        rho3 = rho.reshape(1, *rho.shape) if single else rho
+        if rho3.ndim != 3 or rho3.shape[1] != rho3.shape[2]:
+            raise TypeError("Input state is not a valid operator.")
+        batch, N, _ = rho3.shape
+        xvec = _f64(xvec).reshape(-1)
+        S = len(xvec)
+        out = np.empty((batch, S, S), dtype=np.float64)
+        yvec = np.empty((S,), dtype=np.float64)
+        check(self._lib.bq_wigner_fft_host(self._h, _ptr(rho3), N, N, N * N, batch, _ptr(xvec), S, float(g), _ptr(out),
+                                           _ptr(yvec)))
+        return (out[0] if single else out), yvec
+
+    def wigner_fft_t(self, rho, xvec, g: float = math.sqrt(2), out=None, stream=None):
+        """Device-resident ``method="fft"``: ``rho`` complex128 CUDA tensor, ``xvec`` a HOST array (the p axis is
+        computed from it on the host) -> ``(W tensor, yvec ndarray)``."""
+        import torch
+
+        self._check_tensor(rho, torch.complex128, "rho")
+        single = rho.dim() == 2
+        rho3 = rho.unsqueeze(0) if single else rho
+        batch, N, _ = rho3.shape
+        xvec = _f64(xvec).reshape(-1)
+        S = len(xvec)
+        if out is None:
+            out = torch.empty((batch, S, S), dtype=torch.float64, device=rho.device)
+        else:
+            self._check_tensor(out, torch.float64, "out")
+        yvec = np.empty((S,), dtype=np.float64)
+        check(self._lib.bq_wigner_fft_dev(self._h, ctypes.c_void_p(rho3.data_ptr()), N, N, N * N, batch, _ptr(xvec), S,
+                                          float(g), ctypes.c_void_p(out.data_ptr()), _ptr(yvec), self._stream_ptr(stream)))
+        return (out[0] if single else out), yvec
+
     def state_to_wigner(self, psi, traced: Sequence[int], xvec, yvec=None, g: float = math.sqrt(2),
                         method: str = "clenshaw", return_rho: bool = False, out=None):
-        """Fused frame loop: ``psi`` (dim,) or (frames, dim) -> W (and optionally the reduced rho)."""
+        """Fused frame loop: ``psi`` (dim,) or (frames, dim) -> W (and optionally the reduced rho).
+        ``method="fft"`` returns ``(W, yvec)`` in place of ``W`` (trace, then ``wigner_fft``)."""
         code = method_code(method)
+        if code == METHODS["fft"]:
+            rho_f = self.partial_trace_sv(psi, traced)
+            res = self.wigner_fft(rho_f, xvec, g=g)
+            return (res, rho_f) if return_rho else res
         psi = _c128(psi)
         single = psi.ndim == 1
         psi2 = psi.reshape(1, -1) if single else psi

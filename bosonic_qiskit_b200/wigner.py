@@ -48,11 +48,9 @@ def _simulate(*args, **kwargs):
 
 
 def _check_fft(method):
-    if method_code(method) == 3:
-        raise NotImplementedError(
-            "method='fft' (qutip._wigner_fourier: eigendecomposition + FFT on its own p-axis) is not "
-            "provided by the B200 path; use 'clenshaw', 'iterative' or 'laguerre'"
-        )
+    """``method="fft"`` is served by its own entry point (``bq_wigner_fft_*``): like ``qutip.wigner`` it returns the
+    tuple ``(W, yvec)`` on the p axis it derives from the x grid, wherever the reference would return ``W``."""
+    return method_code(method) == 3
 
 
 def simulate_wigner(
@@ -78,7 +76,6 @@ def simulate_wigner(
         raise RuntimeError("No state vector returned from the simulation")
 
     state = states[conditional_state] if conditional_state else states
-    _check_fft(method)
     traced = _find_qubit_indices(circuit) if trace else []
     xvec = np.asarray(xvec, dtype=np.float64)
     W = get_engine().state_to_wigner(np.asarray(state.data), traced, xvec, None, g=g, method=method)
@@ -107,9 +104,11 @@ def simulate_wigner_multiple_statevectors(
               for num in range(num_statevectors)]
     if not frames:
         return []
-    _check_fft(method)
     traced = _find_qubit_indices(circuit) if trace else []
     W = frames_to_wigner(frames, traced, xvec, g=g, method=method)
+    if _check_fft(method):  # one (W, yvec) tuple per frame, what the reference's loop would collect from qutip
+        W, yvec = W
+        return [(W[k], yvec) for k in range(W.shape[0])]
     return [W[k] for k in range(W.shape[0])]
 
 
@@ -174,7 +173,6 @@ def _wigner(state, xvec, yvec=None, g: float = _SQRT2, method: WignerMethods = "
     if not yvec:  # same truthiness test as the reference (wigner.py:187)
         yvec = xvec
 
-    _check_fft(method)
     if rho.ndim == 1:  # qutip turns kets into density matrices
         rho = np.outer(rho, rho.conj())
     return get_engine().wigner(rho, np.asarray(xvec, dtype=np.float64), np.asarray(yvec, dtype=np.float64), g=g,
@@ -238,8 +236,10 @@ def wigner_projections(circuit, x, y_z, y_x, xvec=None, **wigner_kwargs):
     g = wigner_kwargs.pop("g", _SQRT2)
     if wigner_kwargs:
         raise TypeError(f"_wigner() got an unexpected keyword argument {next(iter(wigner_kwargs))!r}")
-    _check_fft(method)
     W = eng.wigner(np.stack(proj), np.asarray(xvec, dtype=np.float64), None, g=g, method=method)
+    if _check_fft(method):
+        W, yvec = W
+        return (W[0], yvec), (W[1], yvec), (W[2], yvec), (W[3], yvec)
     return W[0], W[1], W[2], W[3]
 
 

@@ -40,12 +40,14 @@ typedef enum bq_status {
     BQ_ERR_INVALID = -1,  /* bad argument (NULL, negative size, bad qubit index, non power of two ...) */
     BQ_ERR_CUDA = -2,     /* a CUDA runtime call failed; see bq_last_error() */
     BQ_ERR_NO_DEVICE = -3,/* no CUDA device / requested ordinal absent */
-    BQ_ERR_UNSUPPORTED = -4 /* e.g. method="fft" */
+    BQ_ERR_UNSUPPORTED = -4 /* e.g. method="fft" handed to a grid entry point (it has its own: bq_wigner_fft_*) */
 } bq_status;
 
 /* qutip.wigner `method=` values (src/bosonic_qiskit/wigner.py:22 WignerMethods).  The three grid
  * methods are the same function evaluated by different recurrences; this library serves all three
- * names from the Clenshaw kernel.  "fft" (different p axis) is not implemented: BQ_ERR_UNSUPPORTED. */
+ * names from the Clenshaw kernel.  "fft" evaluates W on a p axis it derives from the x grid and returns that
+ * axis too, so it has its own entry points (bq_wigner_fft_host / _dev); the grid entry points answer
+ * BQ_WIGNER_FFT with BQ_ERR_UNSUPPORTED. */
 typedef enum bq_wigner_method {
     BQ_WIGNER_CLENSHAW = 0,
     BQ_WIGNER_ITERATIVE = 1,
@@ -112,6 +114,18 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
 int bq_wigner_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
                   const double *d_xvec, int nx, const double *d_yvec, int ny, double g, int method,
                   double *d_W_out, void *stream);
+
+/* method="fft" of qutip.wigner (qutip/wigner.py::_wigner_fourier, reached through
+ * src/bosonic_qiskit/wigner.py:190 with method="fft"): the Fourier transform of <x - s|rho|x + s> along s on the
+ * x grid `xvec` (uniform spacing, nx >= 2), evaluated for all eigenvectors of rho at once (no eigensolver, see
+ * csrc/wigner_fft_kernels.cu).  The whole of rho is read (it need not be Hermitian).
+ *   xvec      HOST pointer in both variants (the p axis is computed from it on the host)
+ *   W_out     batch x nx x nx float64, W[b][ip][ix]
+ *   yvec_out  HOST, nx float64: the p axis of W_out (what qutip returns as the second tuple element)          */
+int bq_wigner_fft_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                       const double *xvec, int nx, double g, double *W_out, double *yvec_out);
+int bq_wigner_fft_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                      const double *xvec, int nx, double g, double *d_W_out, double *yvec_out, void *stream);
 
 /* ---- fused frame loop: psi_k -> rho_k -> W_k for a batch of frames --------------------------- */
 /* Replaces the loop bodies at src/bosonic_qiskit/wigner.py:92-96 and animate.py:326-352

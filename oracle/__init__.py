@@ -24,5 +24,7 @@ from .wigner_np import (  # noqa: F401
     wigner_clenshaw,
     wigner_iterative,
     wigner_laguerre,
+    wigner_fft,
+    osc_eigen,
     flops_per_point,
 )

@@ -163,8 +163,14 @@ def case_wigner_entry_points():
         wigner._wigner(DensityMatrix(rho), np.linspace(-3, 3, 20), yvec=np.linspace(-1, 1, 4))
     with pytest.raises(TypeError):
         wigner.wigner(rho, method="bogus")
-    with pytest.raises(NotImplementedError):
-        wigner.wigner(rho, method="fft")
+    # method="fft": the tuple (W, yvec) qutip.wigner returns for it, on the p axis derived from the x grid
+    from oracle import wigner_fft
+
+    Wf, yf = wigner.wigner(rho, axes_min=-5, axes_max=5, axes_steps=40, method="fft")
+    Wo, yo = wigner_fft(np.asarray(rho), np.linspace(-5, 5, 40))
+    assert Wf.shape == (40, 40) and yf.shape == (40,)
+    np.testing.assert_allclose(yf, yo, rtol=1e-14, atol=0)
+    assert np.abs(Wf - Wo).max() <= 1e-10 * np.abs(Wo).max()
 
 
 def case_wigner_projections():

@@ -44,11 +44,20 @@ class OracleEngine:
         from bosonic_qiskit_b200.engine import method_code
 
         if method_code(method) == 3:
-            raise NotImplementedError
+            return self.wigner_fft(rho, xvec, g)
         rho = np.asarray(rho, dtype=np.complex128)
         if rho.ndim == 2:
             return wigner_clenshaw(rho, xvec, yvec, g)
         return np.stack([wigner_clenshaw(r, xvec, yvec, g) for r in rho])
+
+    def wigner_fft(self, rho, xvec, g=math.sqrt(2)):
+        from oracle import wigner_fft
+
+        rho = np.asarray(rho, dtype=np.complex128)
+        if rho.ndim == 2:
+            return wigner_fft(rho, xvec, g)
+        res = [wigner_fft(r, xvec, g) for r in rho]
+        return np.stack([r[0] for r in res]), res[0][1]
 
     def state_to_wigner(self, psi, traced, xvec, yvec=None, g=math.sqrt(2), method="clenshaw", return_rho=False, out=None):
         psi = np.asarray(psi, dtype=np.complex128)

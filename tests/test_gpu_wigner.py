@@ -103,10 +103,16 @@ def test_bad_method(engine):
     rho = workloads.random_rho(4, seed=0)
     with pytest.raises(TypeError):
         engine.wigner(rho, np.linspace(-1, 1, 4), method="nope")
-    from bosonic_qiskit_b200 import BQError
+    import ctypes
 
-    with pytest.raises(BQError):
-        engine.wigner(rho, np.linspace(-1, 1, 4), method="fft")
+    from bosonic_qiskit_b200._lib import BQ_ERR_UNSUPPORTED
+
+    # the grid entry point itself refuses method code 3 ("fft" has its own entry point, tests/test_gpu_fft.py)
+    x = np.linspace(-1, 1, 4)
+    out = np.empty((1, 4, 4))
+    rc = engine._lib.bq_wigner_host(engine._h, ctypes.c_void_p(rho.ctypes.data), 4, 4, 16, 1, ctypes.c_void_p(x.ctypes.data), 4,
+                                    ctypes.c_void_p(x.ctypes.data), 4, 2 ** 0.5, 3, ctypes.c_void_p(out.ctypes.data))
+    assert rc == BQ_ERR_UNSUPPORTED
 
 
 # ---- analytic known answers (the reference pins no Wigner value) --------------------

@@ -146,3 +146,43 @@ def test_partial_trace_matrix_form_and_dm_branch():
         partial_trace_sv(np.ones(8), [1, 1])
     with pytest.raises(ValueError):
         partial_trace_sv(np.ones(6), [0])
+
+
+def test_fft_method_restatement():
+    """qutip/wigner.py::_wigner_fourier restated (oracle.wigner_fft): qutip's own test criterion (fft against
+    iterative on the fft's p axis, 20 levels, linspace(-10, 10, 128): sum|diff| < 1e-7), the tuple it returns, and
+    the closed form the GPU path evaluates (sum over eigenvectors taken before the transform)."""
+    import numpy as np
+
+    from oracle import osc_eigen, wigner_fft, wigner_iterative
+
+    rng = np.random.default_rng(0)
+    N, x = 20, np.linspace(-10, 10, 128)
+    psi = rng.normal(size=N) + 1j * rng.normal(size=N)
+    psi /= np.linalg.norm(psi)
+    psi2 = rng.normal(size=N) + 1j * rng.normal(size=N)
+    psi2 /= np.linalg.norm(psi2)
+    rho = 0.6 * np.outer(psi, psi.conj()) + 0.4 * np.outer(psi2, psi2.conj())
+    for state in (psi, rho):
+        Wf, y = wigner_fft(state, x)
+        dm = state if state.ndim == 2 else np.outer(state, state.conj())
+        assert Wf.shape == (128, 128) and y.shape == (128,)
+        assert np.abs(wigner_iterative(dm, x, y) - Wf).sum() < 1e-7
+    for S in (52, 53):
+        xs = np.linspace(-7, 7, S)
+        Wf, y = wigner_fft(rho, xs)
+        A = osc_eigen(N, xs)
+        R = A.T @ rho @ A
+        n = 2 * S
+        ks = np.concatenate((np.arange(3 * n // 4, n), np.arange(0, n // 4)))
+        ref = np.zeros((S, S))
+        for i in range(S):
+            m = min(i, S - 1 - i)
+            d = np.arange(-m, m + 1)
+            w = R[i + d, i - d]
+            th = 2 * np.pi * np.outer(ks, d) / n
+            ref[i] = (w.real * np.cos(th) + w.imag * np.sin(th)).sum(axis=1)
+        p = np.arange(-n / 4, n / 4) * np.pi / (n * (xs[1] - xs[0]))
+        ref = (ref / (p[1] - p[0]) / n).T
+        assert np.abs(Wf - ref).max() < 1e-12 * np.abs(Wf).max()
+        np.testing.assert_allclose(y, p, rtol=1e-13)  # (g = sqrt(2): the axis scalings cancel to rounding)
