@@ -67,6 +67,8 @@ struct bq_handle_s {
     std::mutex mu;
     cudaStream_t stream = nullptr;  // used by the _host entry points
     cudaEvent_t ev_order = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device -> host copies of finished frame blocks, overlapped with the next block
+    cudaEvent_t ev_block[4] = {}, ev_copied = nullptr;
     cudaStream_t last_stream = nullptr;
     bool have_last = false;
 
@@ -431,6 +433,12 @@ int bq_create(bq_handle_t *out, int device)
         h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
     }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_block[0], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_block[1], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_block[2], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_block[3], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&h->ev_t0) == cudaSuccess && cudaEventCreate(&h->ev_t1) == cudaSuccess &&
               cudaMalloc(&h->ctr, sizeof(unsigned int) * 2 * kCtrSlots) == cudaSuccess &&
@@ -463,6 +471,10 @@ int bq_destroy(bq_handle_t h)
         if (h->ev_order) cudaEventDestroy(h->ev_order);
         if (h->ev_t0) cudaEventDestroy(h->ev_t0);
         if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+        for (cudaEvent_t e : h->ev_block)
+            if (e) cudaEventDestroy(e);
+        if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+        if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         if (h->stream) cudaStreamDestroy(h->stream);
     }
     delete h;
@@ -890,6 +902,35 @@ int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, cons
     CU(h->rho_dev.reserve(rho_b));
     HostTimer timer(h);
     CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    // Many frames, staged output (symmetric-grid kernels): the frames go in up to 4 blocks and a finished block's
+    // device -> host copy runs on a second stream under the next block's kernel -- the copy (PCIe) is the longer leg
+    // of such a call, so what is hidden is the compute.  Blocks keep >= 2 whole rounds of resident CTAs each.
+    int blocks = 1;
+    if (!direct && out_b >= ((size_t)8 << 20) && batch >= 8 && nx == ny) {
+        const int64_t U = (nx + 1) / 2, units = (int64_t)batch * U * (U + 1) / 2;
+        const int64_t round = (int64_t)h->dev.sm_count * 768;  // units one round of the 3-unit tile covers
+        blocks = (int)std::max<int64_t>(1, std::min<int64_t>({4, units / (2 * round), (int64_t)batch / 2}));
+    }
+    if (blocks > 1 && n_qubits - n_traced <= 14) {
+        const int64_t frame_pts = (int64_t)nx * ny;
+        rc = trace_sv_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, 1, batch, psi_stride,
+                           (double2 *)h->rho_dev.ptr, h->stream);
+        if (rc) return rc;
+        for (int k = 0; k < blocks; ++k) {
+            const int b0 = (int)((int64_t)batch * k / blocks), b1 = (int)((int64_t)batch * (k + 1) / blocks);
+            rc = wigner_core(h, (const double2 *)h->rho_dev.ptr + (int64_t)b0 * D * D, (int)D, D, D * D, b1 - b0, dx, nx, dy, ny,
+                             g, d_out + b0 * frame_pts, h->stream, mirror);
+            if (rc) return rc;
+            CU(cudaEventRecord(h->ev_block[k], h->stream));
+            CU(cudaStreamWaitEvent(h->copy_stream, h->ev_block[k], 0));
+            CU(cudaMemcpyAsync(W_out + b0 * frame_pts, d_out + b0 * frame_pts, (size_t)(b1 - b0) * frame_pts * sizeof(double),
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        if (rho_out) CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, rho_b, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->ev_copied, h->copy_stream));
+        CU(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
+        return timer.finish();
+    }
     rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, batch, psi_stride, dx, nx,
                               dy, ny, g, d_out, (double2 *)h->rho_dev.ptr, h->stream, mirror);
     if (rc) return rc;
