@@ -10,8 +10,9 @@
 //   F[i][k]   = sum_{d=-m_i}^{m_i} R[i+d][i-d] exp(-2 pi i d k / n), m_i = min(i, S-1-i)      (the Toeplitz band of row i)
 //   W[c][i]   = g^2/2 * Re F[i][k_c] / (p_1 - p_0) / n,  k_c = (3n/4 + c) mod n                (the half of the spectrum QuTiP keeps)
 //
-// The transform is evaluated as a banded DFT with an exact twiddle table (one cos/sin pair per residue of d k mod n):
-// S^3 DFMA in all, no power-of-two restriction on S, and only the S frequencies QuTiP returns are computed.
+// The transform is evaluated as a banded DFT: twiddles advance by one complex multiplication per term and are
+// re-read from an exact table (one cos/sin pair per residue of d k mod n) every 32 terms.  S^3 terms in all, no
+// power-of-two restriction on S, and only the S frequencies QuTiP returns are computed.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -144,14 +145,26 @@ __global__ void __launch_bounds__(256) fft_band_dft_kernel(const double2 *__rest
     const int k_first = (3 * n) / 4, n_hi = n - k_first;  // columns [0, n_hi): k = 3n/4 + c;  then k = c - n_hi
     for (int c = threadIdx.x; c < S; c += blockDim.x) {
         const int k = c < n_hi ? k_first + c : c - n_hi;
-        // residue of d k mod n, starting at d = -m
-        int t = (int)((((int64_t)(-m) * k) % n + n) % n);
+        // exp(-i d theta_k), theta_k = 2 pi k / n, is a geometric sequence in d: taken exactly from the table every
+        // kResync terms (residue of d k mod n) and advanced by one complex multiplication in between -- a table
+        // gather per term made this kernel wait on the load/store unit (0.7 TFLOP/s at S = 2048)
+        constexpr int kResync = 32;
+        const double2 wk = __ldg(T + k);
+        int t = (int)((((int64_t)(-m) * k) % n + n) % n);  // residue at d = -m
+        const int t_step = (int)(((int64_t)kResync * k) % n);
         double acc = 0.0;
-        for (int e = 0; e <= 2 * m; ++e) {
-            const double2 w = band[e];
-            const double2 tw = __ldg(T + t);
-            acc = fma(w.x, tw.x, fma(w.y, tw.y, acc));  // Re(w exp(-i theta))
-            t += k;
+        const int len = 2 * m + 1;
+        for (int e0 = 0; e0 < len; e0 += kResync) {
+            double2 z = __ldg(T + t);
+            const int e1 = min(e0 + kResync, len);
+            for (int e = e0; e < e1; ++e) {
+                const double2 w = band[e];
+                acc = fma(w.x, z.x, fma(w.y, z.y, acc));  // Re(w exp(-i d theta))
+                const double zx = fma(z.x, wk.x, -(z.y * wk.y));
+                z.y = fma(z.x, wk.y, z.y * wk.x);
+                z.x = zx;
+            }
+            t += t_step;
             if (t >= n) t -= n;
         }
         W[(int64_t)c * S + i] = acc * scale;

@@ -505,6 +505,13 @@ __device__ __forceinline__ void sym_tail(SymPoints<CL> &s, const double4 t)
     }
 }
 
+// Rotated trip (loads of step r + 4 issued right after step r): measured SLOWER (profiles/r1d_sym_variants_rotated.txt:
+// cutoff 64 / 2048^2 0.575 vs 0.495 ms, cutoff 1024 / 4096^2 459 vs 421 ms) because the SASS re-scheduler leaves a loop
+// with loop-carried loads alone, and its operand-reuse chains are worth more than the hidden LDS latency.  Off.
+#ifndef BQ_SYM_ROTATE
+#define BQ_SYM_ROTATE 0
+#endif
+
 template <int CL>
 __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__restrict__ cd,
                                              const double4 *__restrict__ td, const int K)
@@ -525,6 +532,35 @@ __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__
     int r = 0;
     // four steps per trip: with 5 CL DFMAs per step the loop control and the load latency of a two-step body
     // showed as `wait` stalls (fp64 pipe 72 % busy at N = 256)
+#if BQ_SYM_ROTATE
+    // ... and the trip is ROTATED: the coefficients of step r + 4 are loaded right after step r has consumed its own,
+    // into the same registers, so no trip starts by waiting for shared memory (the loads at the loop top were 20 % of
+    // the stall samples of the cutoff-1024 kernel: two warps per scheduler cannot hide a 29-cycle LDS)
+    if (m >= 4) {
+        double2 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
+        double4 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
+#pragma unroll 1
+        for (; r + 7 < m; r += 4) {
+            sym_step<CL>(s, c0, t0);
+            c0 = cp[r + 4];
+            t0 = tp[r + 4];
+            sym_step<CL>(s, c1, t1);
+            c1 = cp[r + 5];
+            t1 = tp[r + 5];
+            sym_step<CL>(s, c2, t2);
+            c2 = cp[r + 6];
+            t2 = tp[r + 6];
+            sym_step<CL>(s, c3, t3);
+            c3 = cp[r + 7];
+            t3 = tp[r + 7];
+        }
+        sym_step<CL>(s, c0, t0);
+        sym_step<CL>(s, c1, t1);
+        sym_step<CL>(s, c2, t2);
+        sym_step<CL>(s, c3, t3);
+        r += 4;
+    }
+#else
 #pragma unroll 1
     for (; r + 3 < m; r += 4) {
         sym_step<CL>(s, cp[r], tp[r]);
@@ -532,6 +568,7 @@ __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__
         sym_step<CL>(s, cp[r + 2], tp[r + 2]);
         sym_step<CL>(s, cp[r + 3], tp[r + 3]);
     }
+#endif
 #pragma unroll 1
     for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
     sym_tail<CL>(s, tp[m]);
