@@ -57,6 +57,7 @@ SIGNATURES = {
     "bq_set_grid_symmetry": (c_int, [_H, c_int]),
     "bq_set_unit_range": (c_int, [_H, c_int64, c_int64]),
     "bq_grid_units": (c_int64, [c_int]),
+    "bq_set_sym_variant": (c_int, [_H, c_int]),
     "bq_grid_is_mirror": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "bq_device_alloc": (c_int, [_H, c_size_t, POINTER(c_void_p)]),
     "bq_device_free": (c_int, [_H, c_void_p]),

@@ -1027,6 +1027,14 @@ int bq_set_unit_range(bq_handle_t h, int64_t first, int64_t count)
     return BQ_OK;
 }
 
+int bq_set_sym_variant(bq_handle_t h, int variant)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->dev.sym_force = variant < 0 ? -1 : variant;
+    return BQ_OK;
+}
+
 int64_t bq_grid_units(int nx)
 {
     const int64_t U = ((int64_t)nx + 1) / 2;

@@ -8,7 +8,7 @@ namespace bq {
 
 constexpr int kResidentMaxN = 64;  // stream fits twice per SM in shared memory up to this cutoff
 constexpr int kMaxQubits = 40;
-constexpr int kKernelSlots = 40;
+constexpr int kKernelSlots = 48;
 
 // records in the coefficient stream of cutoff N, and the first record of the diagonal with K = N-L
 // coefficients (K >= 2); layout described in bq_common.cuh

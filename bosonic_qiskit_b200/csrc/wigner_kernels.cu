@@ -466,8 +466,15 @@ struct SymPoints {
     double wr[CL][8], wi[CL][8];
 };
 
+// recurrence state only (the ring kernel that parks its Horner accumulators in shared memory)
 template <int CL>
-__device__ __forceinline__ void sym_step(SymPoints<CL> &s, const double2 c, const double4 t)
+struct SymCore {
+    double B[CL], al[CL], be[CL];
+    double y0r[CL], y0i[CL], y1r[CL], y1i[CL];
+};
+
+template <int CL, typename P>
+__device__ __forceinline__ void sym_step(P &s, const double2 c, const double4 t)
 {
 #pragma unroll
     for (int p = 0; p < CL; ++p) {
@@ -512,9 +519,10 @@ __device__ __forceinline__ void sym_tail(SymPoints<CL> &s, const double4 t)
 #define BQ_SYM_ROTATE 0
 #endif
 
-template <int CL>
-__device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__restrict__ cd,
-                                             const double4 *__restrict__ td, const int K)
+// the steps of one diagonal (everything but its tail); returns the tail record
+template <int CL, typename P>
+__device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__restrict__ cd,
+                                                      const double4 *__restrict__ td, const int K)
 {
     {
         const double2 c1 = cd[0], c0 = cd[1];
@@ -571,7 +579,39 @@ __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__
 #endif
 #pragma unroll 1
     for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
-    sym_tail<CL>(s, tp[m]);
+    return tp[m];
+}
+
+template <int CL>
+__device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__restrict__ cd,
+                                             const double4 *__restrict__ td, const int K)
+{
+    const double4 t = sym_diagonal_steps<CL>(s, cd, td, K);
+    sym_tail<CL>(s, t);
+}
+
+// Tail with the eight Horner accumulators of every unit in shared memory, acc[(unit slot * 8 + k) * THREADS + tid]
+// (16 bytes per lane and instruction: conflict-free).  Same arithmetic as sym_tail.
+template <int CL, int THREADS>
+__device__ __forceinline__ void sym_tail_parked(SymCore<CL> &s, const double4 t, double2 *__restrict__ acc)
+{
+#pragma unroll
+    for (int p = 0; p < CL; ++p) {
+        const double tn = fma(s.B[p], t.z, t.y);
+        const double Sr = fma(tn, s.y1r[p], s.y0r[p]);
+        const double Si = fma(tn, s.y1i[p], s.y0i[p]);
+        const double as = s.al[p] * t.z, bs = s.be[p] * t.z;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double pr = (k & 1) ? -((k < 4) ? bs : as) : ((k < 4) ? bs : as);
+            const double pi = (k & 2) ? -((k < 4) ? as : bs) : ((k < 4) ? as : bs);
+            const double2 w = acc[(p * 8 + k) * THREADS];
+            acc[(p * 8 + k) * THREADS] = make_double2(fma(w.x, pr, fma(-w.y, pi, Sr)), fma(w.x, pi, fma(w.y, pr, Si)));
+        }
+        // keep ptxas from hoisting the next unit's 8 accumulator loads above this unit's arithmetic: with all 8 CL of
+        // them in flight the tail, not the loop, set the kernel's register count (255 + spills)
+        asm volatile("" ::: "memory");
+    }
 }
 
 // unit index -> (a, b), a <= b < U;  row a starts at a U - a (a - 1) / 2
@@ -756,6 +796,118 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
     leave_grid(p);
 }
 
+// Ring kernel for large cutoffs with the Horner accumulators PARKED in shared memory.  They are 16 CL doubles per
+// thread that are only touched once per diagonal, yet in registers they cap the kernel at 3 units per thread and
+// 2 warps per scheduler.  Parked (2 x 8 x 16-byte shared-memory accesses per unit and diagonal against
+// 5 (K - 2) DFMA), a thread holds CL = 4 units in ~140 registers: 20 DFMA per step between two rounds of
+// coefficient loads, and room for the re-scheduler's operand-reuse chains.  Two ring stages instead of three pay for
+// the 128 KB of accumulators (a stage is a whole diagonal: its refill hides behind hundreds of steps).
+template <int CL, int THREADS, int STAGES>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184) wigner_sym_diag_parked_kernel(const WigParams p)
+{
+    constexpr int NWARPS = THREADS / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = p.N, cap = N + 1;
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)STAGES * cap * 32);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * cap * 48);
+    uint64_t *empty = full + STAGES;
+    int *slot = reinterpret_cast<int *>(empty + STAGES);
+    const size_t acc_off = ((size_t)STAGES * cap * 48 + 2 * STAGES * 8 + 64 + 15) & ~(size_t)15;
+    const int tid = threadIdx.x;
+    double2 *acc = reinterpret_cast<double2 *>(smem + acc_off) + tid;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t full_phase = 0, fill_count = 0;
+    TileCursor tc{0, 0};
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
+
+        int pg = 0, pK = 2;
+        auto produce = [&]() {
+            const uint32_t st = (uint32_t)pg % STAGES;
+            const int Kend = group_end(pK, pg == 0, cap, N);
+            const int64_t first = (pg == 0) ? 0 : diag_pos(pK);
+            const int64_t last = (Kend <= N) ? diag_pos(Kend) : (int64_t)p.R_tot;
+            const uint32_t recs = (uint32_t)(last - first);
+            mbar_wait(&empty[st], ((fill_count >> st) & 1u) ^ 1u);
+            fill_count ^= 1u << st;
+            mbar_arrive_expect_tx(&full[st], recs * 48u);
+            bulk_g2s(tab_s + (size_t)st * cap, p.tab + first, recs * 32u, &full[st]);
+            bulk_g2s(cs_s + (size_t)st * cap, cs_g + first, recs * 16u, &full[st]);
+            ++pg;
+            pK = Kend;
+        };
+        if (tid == 0)
+            for (int d = 0; d < STAGES - 1 && pK <= N; ++d) produce();
+
+        SymCore<CL> s;
+        int ua[CL], ub[CL];
+        const int64_t chunk = (int64_t)tif * THREADS + tid;
+        bool loaded = false;
+
+        int K = 2;
+        for (int g = 0; K <= N; ++g) {
+            const uint32_t st = (uint32_t)g % STAGES;
+            mbar_wait(&full[st], (full_phase >> st) & 1u);
+            full_phase ^= 1u << st;
+            const double2 *cb = cs_s + (size_t)st * cap;
+            const double4 *tb = tab_s + (size_t)st * cap;
+            int pos = 0;
+            if (!loaded) {
+                const double2 h = cb[0];
+#pragma unroll
+                for (int c = 0; c < CL; ++c) {
+                    const int64_t t = p.sym_first + min(chunk * CL + c, p.sym_units - 1);
+                    sym_unit(t, p.sym_U, ua[c], ub[c]);
+                    s.al[c] = p.g * __ldg(p.xvec + ua[c]);
+                    s.be[c] = p.g * __ldg(p.xvec + ub[c]);
+                    s.B[c] = fma(s.be[c], s.be[c], s.al[c] * s.al[c]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[(c * 8 + k) * THREADS] = h;
+                }
+                loaded = true;
+                pos = 1;
+            }
+            const int Kend = group_end(K, g == 0, cap, N);
+            for (; K < Kend; ++K) {
+                const double4 t = sym_diagonal_steps<CL>(s, cb + pos, tb + pos, K);
+                sym_tail_parked<CL, THREADS>(s, t, acc);
+                pos += K + 1;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+            if (tid == 0 && pK <= N) produce();
+        }
+        double *Wf = p.W + (int64_t)frame * p.w_stride;
+        const int S = p.nx;
+#pragma unroll
+        for (int c = 0; c < CL; ++c) {
+            if (chunk * CL + c >= p.sym_units) continue;
+            const double e = exp(-0.5 * s.B[c]) * p.scale;
+            const int a = ua[c], b = ub[c], am = S - 1 - a, bm = S - 1 - b;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i1 = (k & 1) ? ((k < 4) ? bm : am) : ((k < 4) ? b : a);   // ix
+                const int i2 = (k & 2) ? ((k < 4) ? am : bm) : ((k < 4) ? a : b);   // iy
+                Wf[(int64_t)i2 * S + i1] = acc[(c * 8 + k) * THREADS].x * e;
+            }
+        }
+    }
+    leave_grid(p);
+}
+
 // ------------------------------------------------------------------------------------------------
 // N > 64: coefficient stream pulled through a shared-memory ring by bulk copies
 // ------------------------------------------------------------------------------------------------
@@ -892,7 +1044,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 19;
+constexpr int kVariants = 21;
 constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
@@ -915,6 +1067,8 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_sym_diag_kernelILi1ELi256ELi3EEEvNS_9WigParamsE",
     "_ZN2bq26wigner_sym_resident_kernelILi4ELi256ELi1EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_sym_diag_kernelILi4ELi256ELi3EEEvNS_9WigParamsE",
+    "_ZN2bq29wigner_sym_diag_parked_kernelILi4ELi256ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq29wigner_sym_diag_parked_kernelILi3ELi384ELi2EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -1029,6 +1183,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             const void *plain;
             int variant, cl, threads;
             double eff;
+            int stages = kDiagStages, parked = 0;  // ring kernels: stages of the ring; Horner accumulators in shared memory
         };
         static const SymVariant resident_variants[] = {
             {(const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 3, 128, 1.00},
@@ -1044,32 +1199,44 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.96},
             {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 16, 1, 256, 0.60},
             {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 18, 4, 256, 0.90},
+            {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2>, 19, 4, 256, 1.00, 2, 1},
+            {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2>, 20, 3, 384, 0.78, 2, 1},
         };
         const bool resident = p.N <= kResidentMaxN;
-        const size_t smem = resident ? (size_t)p.R_tot * 48 + 64 : (size_t)kDiagStages * (p.N + 1) * 48 + 2 * kDiagStages * 8 + 64;
+        auto smem_of = [&](const SymVariant &v) -> size_t {
+            if (resident) return (size_t)p.R_tot * 48 + 64;
+            const size_t ring = (size_t)v.stages * (p.N + 1) * 48 + 2 * v.stages * 8 + 64;
+            return v.parked ? ((ring + 15) & ~(size_t)15) + (size_t)v.cl * 8 * v.threads * sizeof(double2) : ring;
+        };
         const SymVariant *vars = resident ? resident_variants : ring_variants;
-        const int nvars = resident ? 6 : 5;
+        const int nvars = resident ? 6 : 7;
         struct Cand {
             const SymVariant *v;
+            size_t smem;
             int occ;
             int64_t ctas, tiles;
             double round_cost;  // one round of resident CTAs: units per SM / how busy the variant keeps the fp64 pipe
         };
-        Cand cand[6];
+        Cand cand[7];
         int ncand = 0;
-        if (smem <= dev.smem_optin && (resident || p.sym_want_count >= 0 || units >= 2LL * 256 * (dev.sm_count / 2))) {
+        if (resident || p.sym_want_count >= 0 || units >= 2LL * 256 * (dev.sm_count / 2)) {
             for (int i = 0; i < nvars; ++i) {
                 const SymVariant &v = vars[i];
                 const void *func = nullptr;
                 int occ = 0;
+                const size_t smem = smem_of(v);
+                if (smem > dev.smem_optin) continue;
                 if (occupancy(v.plain, v.variant, v.threads, smem, dev, &func, &occ) != cudaSuccess) {
                     cudaGetLastError();
                     continue;
                 }
-                // (the 2-unit tile loses ~6 % to the 3-unit one at cutoff 64 and wins ~5 % at cutoff <= 32)
-                const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93 : v.eff;
+                // (the 2-unit tile loses ~6 % to the 3-unit one at cutoff 64 and wins ~5 % at cutoff <= 32; parked
+                // accumulators cost 16 shared-memory accesses per unit and diagonal: 0.92 of the 3-unit ring tile at
+                // cutoff 128, 0.99 at 256, 1.09 at 1024 -- profiles/r1d_sym_variants_parked.txt)
+                const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93 : v.parked ? v.eff * (1.10 - 23.0 / p.N) : v.eff;
                 Cand &c = cand[ncand++];
                 c.v = &v;
+                c.smem = smem;
                 c.occ = occ;
                 c.ctas = (int64_t)occ * dev.sm_count;
                 c.tiles = (((p.sym_units + v.cl - 1) / v.cl + v.threads - 1) / v.threads) * p.batch;
@@ -1080,7 +1247,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             WigParams q = p;
             q.sym_first = first;
             q.sym_units = count;
-            return run(v.plain, v.variant, v.threads, smem, q, v.cl, dev, st, launches, (count + v.cl - 1) / v.cl);
+            return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, (count + v.cl - 1) / v.cl);
         };
         // A last round that fills only part of the machine still costs a whole tile.  Tried and measured (tools/
         // sym_split_sweep.py, profiles/r1d_sym_split.txt): whole rounds in one launch and the remainder in a SECOND

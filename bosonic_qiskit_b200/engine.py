@@ -113,6 +113,10 @@ class Engine:
             self._grid_sharing = bool(on)
             check(self._lib.bq_set_grid_symmetry(self._h, 1 if on else 0))
 
+    def set_sym_variant(self, variant: int | None) -> None:
+        """Tuning / test aid: only this variant of the symmetric-grid kernels (None: the library's own choice)."""
+        check(self._lib.bq_set_sym_variant(self._h, -1 if variant is None else int(variant)))
+
     def grid_is_mirror(self, xvec, yvec=None) -> bool:
         """The library's own test of a host grid (``bq_grid_is_mirror``)."""
         x = _f64(xvec).reshape(-1)

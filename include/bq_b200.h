@@ -179,6 +179,10 @@ int bq_set_grid_symmetry(bq_handle_t h, int mode);
  * range is set fails with BQ_ERR_UNSUPPORTED (shard by row slab instead).                               */
 int bq_set_unit_range(bq_handle_t h, int64_t first, int64_t count);
 int64_t bq_grid_units(int nx);
+/* Tuning / test aid: restrict the symmetric-grid kernels to ONE variant of csrc/wigner_kernels.cu's variant table
+ * (its id; -1 = the library's own choice by predicted duration).  A variant that cannot run the call (cutoff class,
+ * shared memory) leaves the point-by-point kernels to do it.  Same as the environment variable BQ_B200_SYM_VARIANT. */
+int bq_set_sym_variant(bq_handle_t h, int variant);
 /* 1 if nx == ny >= 2, yvec[i] == xvec[i] and |xvec[i] + xvec[nx-1-i]| <= 4 ulp of max|xvec|; else 0 */
 int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny);
 

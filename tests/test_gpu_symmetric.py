@@ -181,3 +181,32 @@ def test_grid_verdict_follows_the_tensor_not_its_address(engine):
     W = engine.wigner_t(rho_t, x_t).cpu().numpy()
     assert rel_err(W, wigner_clenshaw(rho, grids[1])) < TOL
     assert len(seen) < len(grids)  # the allocator did recycle an address (otherwise this test shows nothing)
+
+
+RESIDENT_VARIANTS = [8, 9, 11, 12, 13, 17]
+RING_VARIANTS = [10, 14, 15, 16, 18, 19, 20]
+
+
+@pytest.mark.parametrize("variant", RESIDENT_VARIANTS + RING_VARIANTS)
+def test_every_symmetric_kernel_variant(engine, variant):
+    """The library picks a variant by predicted duration, so some run only on particular grids: force each one
+    (bq_set_sym_variant) on an even and an odd grid and check it against the oracle and the point-by-point kernels."""
+    N = 24 if variant in RESIDENT_VARIANTS else 80
+    rho = workloads.random_rho(N, seed=variant, rank=3)
+    try:
+        engine.set_sym_variant(variant)
+        for S in (577, 640):
+            x = np.linspace(-5.5, 5.5, S)
+            before = engine.launches
+            W = np.array(engine.wigner(rho, x))
+            assert engine.launches > before
+            rows = np.arange(0, S, 37)
+            ref = wigner_clenshaw(rho, x, x[rows])
+            assert rel_err(W[rows], ref) < TOL
+            engine.set_grid_sharing(False)
+            Wp = np.array(engine.wigner(rho, x))
+            engine.set_grid_sharing(True)
+            assert rel_err(W, Wp) < 1e-12
+    finally:
+        engine.set_grid_sharing(True)
+        engine.set_sym_variant(None)
