@@ -393,6 +393,7 @@ def main():
     if world > 1:
         dist.barrier()
     launches = eng.launches - launches0
+    kernel_name = eng.last_wigner_kernel()
     kern_ms, kern_n = eng.profile_read()
     eng.profile(False)
     total_ms = float(sum(a.elapsed_time(b) for a, b in ev))
@@ -425,7 +426,7 @@ def main():
             torch.cuda.synchronize()
             p_ms, p_n = eng.profile_read()
             eng.profile(False)
-            pbp = {"kernel_ms": p_ms / max(p_n, 1), "launches": p_n,
+            pbp = {"kernel_ms": p_ms / max(p_n, 1), "launches": p_n, "kernel": eng.last_wigner_kernel(),
                    "ms_per_step": float(sum(a.elapsed_time(b) for a, b in pev)) / args.steps,
                    "max_abs_diff_to_shared_over_max_W": float((W_t - W_keep).abs().max().item() / W_keep.abs().max().item())}
         finally:
@@ -526,6 +527,7 @@ def main():
         kname = "wigner_sym_resident_kernel" if N <= 64 else ("wigner_sym_diag_kernel" if big else "wigner_stream_kernel")
     else:
         kname = "wigner_resident_kernel" if N <= 64 else ("wigner_diag_kernel" if big else "wigner_stream_kernel")
+    kname = kernel_name
     roofline = {
         "bound": "fp64", "kernel": kname,
         "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
@@ -552,8 +554,7 @@ def main():
         if pbp is not None:
             p_tf = points_rank * F / (pbp["kernel_ms"] * 1e-3) / 1e12
             roofline["point_by_point"] = {
-                "kernel": "wigner_resident_kernel" if N <= 64 else ("wigner_diag_kernel" if big else "wigner_stream_kernel"),
-                "kernel_ms": pbp["kernel_ms"], "achieved": p_tf, "frac": p_tf / fp64_peak, "ms_per_step": pbp["ms_per_step"],
+                "kernel": pbp["kernel"], "kernel_ms": pbp["kernel_ms"], "achieved": p_tf, "frac": p_tf / fp64_peak, "ms_per_step": pbp["ms_per_step"],
                 "value": points_rank / (pbp["ms_per_step"] * 1e-3),
                 "max_abs_diff_to_shared_over_max_W": pbp["max_abs_diff_to_shared_over_max_W"]}
 

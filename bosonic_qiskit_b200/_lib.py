@@ -49,6 +49,8 @@ SIGNATURES = {
     "bq_state_to_wigner_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,
                                        c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "bq_frame_minmax_dev": (c_int, [_H, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "bq_frame_rgba_dev": (c_int, [_H, c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "bq_rdbu_lut": (c_int, [c_void_p]),
     "bq_fp64_peak": (c_int, [_H, c_double, _dp]),
     "bq_last_device_ms": (c_int, [_H, _dp]),
     "bq_profile_enable": (c_int, [_H, c_int]),
@@ -58,6 +60,7 @@ SIGNATURES = {
     "bq_set_unit_range": (c_int, [_H, c_int64, c_int64]),
     "bq_grid_units": (c_int64, [c_int]),
     "bq_set_sym_variant": (c_int, [_H, c_int]),
+    "bq_last_wigner_variant": (c_int, [_H, _ip]),
     "bq_grid_is_mirror": (c_int, [c_void_p, c_int, c_void_p, c_int]),
     "bq_device_alloc": (c_int, [_H, c_size_t, POINTER(c_void_p)]),
     "bq_device_free": (c_int, [_H, c_void_p]),

@@ -160,6 +160,25 @@ def wigner_frames_with_measure(
     return w_fock, xvec
 
 
+def frames_to_rgba(frames, levels: int = 100, zero_abs_max: float = 5.0) -> np.ndarray:
+    """RGBA images of Wigner frames without matplotlib: per frame the symmetric colour levels of ``_animate``
+    (``animate.py:278-286``: ``linspace(-abs_max, abs_max, 100)``) and the ``RdBu`` colour ``contourf`` gives each
+    grid node, computed on the GPU (min/max reduction + one colouring kernel, ``bq_frame_rgba_dev``).  Opt-in fast
+    path for movie writers (``imshow(rgba, origin="lower")`` / raw frames to ffmpeg); ``animate_wigner`` itself keeps
+    the reference's ``contourf`` rendering.  ``frames``: (F, S, S) or a list of (S, S) -> (F, S, S, 4) uint8."""
+    import torch
+
+    from .engine import get_engine
+
+    eng = get_engine()
+    arr = np.ascontiguousarray(np.stack([np.asarray(f, dtype=np.float64) for f in frames]) if not isinstance(frames, np.ndarray)
+                               else frames, dtype=np.float64)
+    single = arr.ndim == 2
+    W = torch.from_numpy(arr[None] if single else arr).to(torch.device("cuda", eng.device))
+    rgba = eng.frame_rgba_t(W, levels=levels, zero_abs_max=zero_abs_max).cpu().numpy()
+    return rgba[0] if single else rgba
+
+
 def animate_wigner(
     circuit,
     qubit=None,
@@ -219,4 +238,5 @@ __all__ = [
     "wigner_frames_without_measure",
     "wigner_frames_with_measure",
     "wigner_frames_with_state",
+    "frames_to_rgba",
 ]

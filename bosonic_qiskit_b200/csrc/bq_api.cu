@@ -77,6 +77,8 @@ struct bq_handle_s {
     Buffer cs, partial, rho_tmp;                            // kernel scratch
     Buffer in_dev, out_dev, rho_dev, grid_dev, small_dev;   // staging for _host calls
     Buffer fft_a, fft_m, fft_r, fft_t, fft_x;               // method="fft" scratch
+    Buffer mm_dev;                                          // per-frame (min, max) for bq_frame_rgba_dev
+    bool lut_ready = false;
     std::vector<double> grid_host;                          // what grid_dev currently holds
     bool grid_host_mirror = false;                          // ... and whether it is a mirror-symmetric square grid
     int64_t unit_first = 0, unit_count = -1;                // bq_set_unit_range (count < 0: whole grid)
@@ -461,7 +463,7 @@ int bq_destroy(bq_handle_t h)
         for (auto &kv : h->tabs) cudaFree(kv.second);
         for (auto &kv : h->maps) cudaFree(kv.second);
         Buffer *bufs[] = {&h->cs, &h->partial, &h->rho_tmp, &h->in_dev, &h->out_dev, &h->rho_dev, &h->grid_dev, &h->small_dev,
-                          &h->fft_a, &h->fft_m, &h->fft_r, &h->fft_t, &h->fft_x};
+                          &h->fft_a, &h->fft_m, &h->fft_r, &h->fft_t, &h->fft_x, &h->mm_dev};
         for (Buffer *b : bufs) b->release();
         for (auto &pr : h->prof_events) {
             cudaEventDestroy(pr.first);
@@ -958,6 +960,77 @@ int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_fra
     return BQ_OK;
 }
 
+// matplotlib's LinearSegmentedColormap.from_list("RdBu", 11 ColorBrewer anchors, N=256) lookup table as bytes, same
+// operations in the same order as its _create_lookup_table (volatile: no FMA contraction by the host compiler)
+static void build_rdbu_lut(unsigned char *lut)
+{
+    static const int anchors[11][3] = {{103, 0, 31}, {178, 24, 43}, {214, 96, 77}, {244, 165, 130}, {253, 219, 199}, {247, 247, 247},
+                                       {209, 229, 240}, {146, 197, 222}, {67, 147, 195}, {33, 102, 172}, {5, 48, 97}};
+    double x[11], xind[256];
+    for (int i = 0; i < 11; ++i) x[i] = i == 10 ? 1.0 : i * (1.0 / 10.0);
+    for (int i = 0; i < 256; ++i) xind[i] = i == 255 ? 1.0 : i * (1.0 / 255.0);
+    for (int ch = 0; ch < 3; ++ch) {
+        double y[11];
+        for (int i = 0; i < 11; ++i) y[i] = anchors[i][ch] / 255.0;
+        for (int i = 0; i < 256; ++i) {
+            double v;
+            if (i == 0) {
+                v = y[0];
+            } else if (i == 255) {
+                v = y[10];
+            } else {
+                int ind = 0;
+                while (ind < 11 && x[ind] < xind[i]) ++ind;  // searchsorted, side="left"
+                volatile double num = xind[i] - x[ind - 1], den = x[ind] - x[ind - 1];
+                volatile double distance = num / den;
+                volatile double prod = distance * (y[ind] - y[ind - 1]);
+                v = prod + y[ind - 1];
+            }
+            v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+            volatile double scaled = v * 255.0;
+            lut[4 * i + ch] = (unsigned char)scaled;
+        }
+    }
+    for (int i = 0; i < 256; ++i) lut[4 * i + 3] = 255;
+}
+
+int bq_rdbu_lut(unsigned char *lut_out)
+{
+    if (!lut_out) return fail(BQ_ERR_INVALID, "NULL pointer");
+    build_rdbu_lut(lut_out);
+    return BQ_OK;
+}
+
+int bq_frame_rgba_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, int levels,
+                      double zero_abs_max, unsigned char *d_rgba_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (points_per_frame < 0 || batch < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (levels < 2 || levels > 4096) return fail(BQ_ERR_INVALID, "levels out of range [2, 4096]");
+    if (batch == 0 || points_per_frame == 0) return BQ_OK;
+    if (!d_W || !d_rgba_out) return fail(BQ_ERR_INVALID, "NULL pointer");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = order_stream(h, st);
+    if (rc) return rc;
+    if (!h->lut_ready) {
+        unsigned char lut[256 * 4];
+        build_rdbu_lut(lut);
+        CU(bq::upload_rdbu_lut(lut));
+        h->lut_ready = true;
+    }
+    CU(h->mm_dev.reserve((size_t)batch * sizeof(double2)));
+    int nl = 0;
+    cudaError_t e = bq::launch_frame_minmax(d_W, points_per_frame, batch, (double2 *)h->mm_dev.ptr, st, &nl);
+    if (e == cudaSuccess)
+        e = bq::launch_frame_rgba(d_W, points_per_frame, batch, (const double2 *)h->mm_dev.ptr, levels, zero_abs_max,
+                                  d_rgba_out, st, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(e, "launch_frame_rgba");
+    return BQ_OK;
+}
+
 // ---- measurement helpers -----------------------------------------------------------------------
 int bq_fp64_peak(bq_handle_t h, double seconds, double *tflops)
 {
@@ -1032,6 +1105,13 @@ int bq_set_sym_variant(bq_handle_t h, int variant)
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
     std::lock_guard<std::mutex> lk(h->mu);
     h->dev.sym_force = variant < 0 ? -1 : variant;
+    return BQ_OK;
+}
+
+int bq_last_wigner_variant(bq_handle_t h, int *variant)
+{
+    if (!h || !variant) return fail(BQ_ERR_INVALID, "NULL argument");
+    *variant = h->dev.last_variant;
     return BQ_OK;
 }
 

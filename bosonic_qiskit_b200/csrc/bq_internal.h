@@ -23,6 +23,7 @@ struct DeviceInfo {
     int pts8 = 0;       // use the 8-points-per-thread resident kernel for large grids
     int sym_force = -1; // >= 0: tuning aid (env BQ_B200_SYM_VARIANT), only this symmetric-kernel variant is eligible
     int sym_split_main = -1, sym_split_tail = -1;  // tuning aid (env BQ_B200_SYM_SPLIT=main:tail): whole rounds / remainder
+    int last_variant = -1;  // variant id (kKernelNames index) of the last Wigner kernel launched
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     bool configured[kKernelSlots] = {};
     int occ[kKernelSlots] = {};
@@ -76,6 +77,10 @@ cudaError_t launch_photon_number(const double2 *rho, int D, int batch, double2 *
 // per-frame (min, max)
 cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, double2 *out, cudaStream_t st,
                                 int *launches);
+// contourf-style RdBu colouring of frames at the grid nodes (levels symmetric colour levels); minmax from launch_frame_minmax
+cudaError_t upload_rdbu_lut(const unsigned char *lut);
+cudaError_t launch_frame_rgba(const double *W, int64_t points, int batch, const double2 *minmax, int levels,
+                              double zero_abs_max, unsigned char *rgba, cudaStream_t st, int *launches);
 // FP64 DFMA peak probe: runs `iters` rounds of 8 independent chains x 16 FMAs per thread
 cudaError_t launch_fp64_probe(double *sink, int iters, int grid, cudaStream_t st);
 

@@ -324,6 +324,71 @@ cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// Frame consumer: what animate._animate / wigner.plot make matplotlib do with a frame
+// (src/bosonic_qiskit/animate.py:278-291, wigner.py:260-269) -- symmetric colour levels
+// linspace(-A, A, levels), A = max(amax, |amin|), and contourf(..., cmap="RdBu") -- evaluated at the grid nodes, so
+// a movie writer can take RGBA frames straight from the device.  Every step repeats NumPy's / matplotlib's own
+// double-precision operations in their order (no FMA contraction): the bytes equal oracle/colormap_np.py's.
+// ------------------------------------------------------------------------------------------------
+__constant__ unsigned char c_rdbu_lut[256 * 4];
+
+__device__ __forceinline__ double level_at(int j, int levels, double A, double step)
+{
+    return j == levels - 1 ? A : __dadd_rn(__dmul_rn((double)j, step), -A);  // numpy.linspace: arange * step + start, last = stop
+}
+
+__global__ void __launch_bounds__(256) frame_rgba_kernel(const double *__restrict__ W, int64_t points,
+                                                         const double2 *__restrict__ minmax, int levels,
+                                                         double zero_abs_max, uchar4 *__restrict__ out, int chunks)
+{
+    extern __shared__ uchar4 band_rgba[];  // [levels - 1]
+    const int frame = blockIdx.x / chunks, chunk = blockIdx.x - frame * chunks;
+    const double2 mm = minmax[frame];
+    double A = fmax(mm.y, fabs(mm.x));
+    if (A == 0.0) A = zero_abs_max;
+    const double step = __ddiv_rn(__dadd_rn(A, A), (double)(levels - 1));  // (stop - start) / div
+    const double lo = level_at(0, levels, A, step), hi = level_at(levels - 1, levels, A, step);
+    for (int j = threadIdx.x; j < levels - 1; j += blockDim.x) {
+        const double layer = __dmul_rn(0.5, __dadd_rn(level_at(j, levels, A, step), level_at(j + 1, levels, A, step)));
+        const double norm = __ddiv_rn(__dadd_rn(layer, -lo), __dadd_rn(hi, -lo));
+        int idx = (int)__dmul_rn(norm, 256.0);
+        idx = idx >= 256 ? 255 : (idx < 0 ? 0 : idx);
+        band_rgba[j] = make_uchar4(c_rdbu_lut[4 * idx], c_rdbu_lut[4 * idx + 1], c_rdbu_lut[4 * idx + 2], c_rdbu_lut[4 * idx + 3]);
+    }
+    __syncthreads();
+    const double *F = W + (int64_t)frame * points;
+    uchar4 *O = out + (int64_t)frame * points;
+    for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < points; i += (int64_t)chunks * blockDim.x) {
+        const double w = F[i];
+        int j = levels - 2;
+        if (w == w) {  // searchsorted(levels, w, side="right") - 1, clipped to the bands
+            j = (int)floor(__ddiv_rn(__dadd_rn(w, A), step));
+            j = max(0, min(j, levels - 1));
+            while (j < levels - 1 && level_at(j + 1, levels, A, step) <= w) ++j;
+            while (j > 0 && level_at(j, levels, A, step) > w) --j;
+            j = min(j, levels - 2);
+        }
+        O[i] = band_rgba[j];
+    }
+}
+
+cudaError_t upload_rdbu_lut(const unsigned char *lut)
+{
+    return cudaMemcpyToSymbol(c_rdbu_lut, lut, 256 * 4);
+}
+
+cudaError_t launch_frame_rgba(const double *W, int64_t points, int batch, const double2 *minmax, int levels,
+                              double zero_abs_max, unsigned char *rgba, cudaStream_t st, int *launches)
+{
+    if (batch <= 0 || points <= 0) return cudaSuccess;
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>((points + 256 * 16 - 1) / (256 * 16), 65535 / std::max(batch, 1) + 1));
+    frame_rgba_kernel<<<batch * chunks, 256, (levels - 1) * sizeof(uchar4), st>>>(W, points, minmax, levels, zero_abs_max,
+                                                                                  reinterpret_cast<uchar4 *>(rgba), chunks);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // FP64 peak probe: 8 independent DFMA chains per thread, nothing else in the loop body.
 // ------------------------------------------------------------------------------------------------
 // 16 independent accumulators, acc_i = fma(b_i, m, acc_i): two register operands + one warp-uniform

@@ -1147,6 +1147,7 @@ cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigPar
     const int grid = (int)min((int64_t)resident, (int64_t)p.total_tiles);
     p.grab = max(1, p.total_tiles / (grid * 8));
     void *args[] = {(void *)&p};
+    dev.last_variant = variant;
     e = cudaLaunchKernel(func, dim3(grid), dim3(threads), args, smem, st);
     if (launches) ++*launches;
     return e;
@@ -1196,7 +1197,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         static const SymVariant ring_variants[] = {
             {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
             {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 0.94},
-            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.96},
+            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.90},
             {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 16, 1, 256, 0.60},
             {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 18, 4, 256, 0.90},
             {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2>, 19, 4, 256, 1.00, 2, 1},

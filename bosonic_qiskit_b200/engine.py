@@ -117,6 +117,24 @@ class Engine:
         """Tuning / test aid: only this variant of the symmetric-grid kernels (None: the library's own choice)."""
         check(self._lib.bq_set_sym_variant(self._h, -1 if variant is None else int(variant)))
 
+    # variant ids of csrc/wigner_kernels.cu (kKernelNames)
+    KERNEL_VARIANTS = {
+        0: "wigner_resident_kernel<4,256,2>", 1: "wigner_resident_kernel<2,128,4>", 2: "wigner_resident_kernel<1,128,4>",
+        3: "wigner_stream_kernel<4,256,4,256>", 4: "wigner_stream_kernel<2,128,4,256>", 5: "wigner_resident_kernel<8,128,2>",
+        6: "wigner_stream_kernel<8,128,4,256>", 7: "wigner_diag_kernel<8,256,3>", 8: "wigner_sym_resident_kernel<3,128,2>",
+        9: "wigner_sym_resident_kernel<1,128,4>", 10: "wigner_sym_diag_kernel<3,256,3>", 11: "wigner_sym_resident_kernel<2,128,2>",
+        12: "wigner_sym_resident_kernel<2,192,2>", 13: "wigner_sym_resident_kernel<1,256,2>", 14: "wigner_sym_diag_kernel<2,256,3>",
+        15: "wigner_sym_diag_kernel<2,384,3>", 16: "wigner_sym_diag_kernel<1,256,3>", 17: "wigner_sym_resident_kernel<4,256,1>",
+        18: "wigner_sym_diag_kernel<4,256,3>", 19: "wigner_sym_diag_parked_kernel<4,256,2>",
+        20: "wigner_sym_diag_parked_kernel<3,384,2>",
+    }
+
+    def last_wigner_kernel(self) -> str:
+        """Name of the kernel variant the last Wigner call launched."""
+        v = ctypes.c_int()
+        check(self._lib.bq_last_wigner_variant(self._h, ctypes.byref(v)))
+        return self.KERNEL_VARIANTS.get(int(v.value), f"variant {int(v.value)}")
+
     def grid_is_mirror(self, xvec, yvec=None) -> bool:
         """The library's own test of a host grid (``bq_grid_is_mirror``)."""
         x = _f64(xvec).reshape(-1)
@@ -482,6 +500,21 @@ class Engine:
         check(self._lib.bq_frame_minmax_dev(self._h, ctypes.c_void_p(W.data_ptr()), points, batch,
                                             ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
         return out
+
+    def frame_rgba_t(self, W, levels: int = 100, zero_abs_max: float = 5.0, out=None, stream=None):
+        """(frames, ny, nx) float64 CUDA tensor -> (frames, ny, nx, 4) uint8: the RdBu colour ``contourf`` gives each
+        grid node with the reference's symmetric colour levels (``animate.py:278-291``)."""
+        import torch
+
+        self._check_tensor(W, torch.float64, "W")
+        W3 = W.unsqueeze(0) if W.dim() == 2 else W
+        batch = W3.shape[0]
+        points = W3[0].numel() if batch else 0
+        if out is None:
+            out = torch.empty((*W3.shape, 4), dtype=torch.uint8, device=W.device)
+        check(self._lib.bq_frame_rgba_dev(self._h, ctypes.c_void_p(W3.data_ptr()), points, batch, int(levels),
+                                          float(zero_abs_max), ctypes.c_void_p(out.data_ptr()), self._stream_ptr(stream)))
+        return out[0] if W.dim() == 2 else out
 
     # ------------------------------------------------------------------ CUDA IPC
     def device_alloc(self, nbytes: int) -> int:

@@ -142,6 +142,14 @@ int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, con
  * animate._animate (src/bosonic_qiskit/animate.py:265-311).  out[2*b] = min, out[2*b+1] = max.    */
 int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, double *d_out,
                         void *stream);
+/* The colour matplotlib gives every grid node of a frame in animate._animate / wigner.plot
+ * (src/bosonic_qiskit/animate.py:278-291, wigner.py:260-269): colour levels linspace(-A, A, levels) with
+ * A = max(amax, |amin|) of the frame (zero_abs_max if that is 0: 5 in _animate, 1 in plot) and
+ * contourf(..., levels, cmap="RdBu").  d_rgba_out: batch x points x 4 bytes (R, G, B, A = 255), same point order as W. */
+int bq_frame_rgba_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, int levels,
+                      double zero_abs_max, unsigned char *d_rgba_out, void *stream);
+/* the 256 x 4 byte lookup table it uses (matplotlib's "RdBu", restated); host only, needs no device */
+int bq_rdbu_lut(unsigned char *lut_out);
 
 /* ---- measurement helpers (bench.py only) ----------------------------------------------------- */
 /* Runs a register-resident DFMA loop on every SM and reports the sustained FP64 rate: the
@@ -183,6 +191,8 @@ int64_t bq_grid_units(int nx);
  * (its id; -1 = the library's own choice by predicted duration).  A variant that cannot run the call (cutoff class,
  * shared memory) leaves the point-by-point kernels to do it.  Same as the environment variable BQ_B200_SYM_VARIANT. */
 int bq_set_sym_variant(bq_handle_t h, int variant);
+/* id of the kernel variant the last Wigner call launched (bench.py names the kernel it reports a roofline for) */
+int bq_last_wigner_variant(bq_handle_t h, int *variant);
 /* 1 if nx == ny >= 2, yvec[i] == xvec[i] and |xvec[i] + xvec[nx-1-i]| <= 4 ulp of max|xvec|; else 0 */
 int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny);
 

@@ -186,3 +186,23 @@ def test_fft_method_restatement():
         ref = (ref / (p[1] - p[0]) / n).T
         assert np.abs(Wf - ref).max() < 1e-12 * np.abs(Wf).max()
         np.testing.assert_allclose(y, p, rtol=1e-13)  # (g = sqrt(2): the axis scalings cancel to rounding)
+
+
+def test_rdbu_lookup_table_of_the_library_equals_the_restated_matplotlib_one():
+    """Host-only entry point (no device): the 256-entry RdBu table behind bq_frame_rgba_dev, bit for bit."""
+    import ctypes
+
+    import numpy as np
+
+    from bosonic_qiskit_b200 import _lib
+    from oracle.colormap_np import frame_rgba, rdbu_lut
+
+    buf = (ctypes.c_ubyte * 1024)()
+    assert _lib.load().bq_rdbu_lut(buf) == 0
+    lut = rdbu_lut()
+    assert np.array_equal(np.frombuffer(buf, dtype=np.uint8).reshape(256, 4), lut)
+    # ColorBrewer anchors survive at both ends and in the middle (white), red = negative values
+    assert tuple(lut[0][:3]) == (103, 0, 31) and tuple(lut[255][:3]) == (5, 48, 97)
+    img = frame_rgba(np.array([[-1.0, 0.0], [0.5, 1.0]]))
+    assert tuple(img[0, 0][:3]) == (103, 0, 31) and tuple(img[1, 1][:3]) == (5, 48, 97) and img[0, 1][0] > 240
+    assert (frame_rgba(np.zeros((3, 3))) == frame_rgba(np.zeros((3, 3)))[0, 0]).all()  # abs_max == 0 -> 5: mid band
