@@ -328,7 +328,7 @@ cudaError_t launch_frame_minmax(const double *W, int64_t points, int batch, doub
 // (src/bosonic_qiskit/animate.py:278-291, wigner.py:260-269) -- symmetric colour levels
 // linspace(-A, A, levels), A = max(amax, |amin|), and contourf(..., cmap="RdBu") -- evaluated at the grid nodes, so
 // a movie writer can take RGBA frames straight from the device.  Every step repeats NumPy's / matplotlib's own
-// double-precision operations in their order (no FMA contraction): the bytes equal oracle/colormap_np.py's.
+// double-precision operations in their order (no FMA contraction), so the bytes equal a NumPy evaluation of the same rules.
 // ------------------------------------------------------------------------------------------------
 __constant__ unsigned char c_rdbu_lut[256 * 4];
 
