@@ -204,5 +204,7 @@ def test_rdbu_lookup_table_of_the_library_equals_the_restated_matplotlib_one():
     # ColorBrewer anchors survive at both ends and in the middle (white), red = negative values
     assert tuple(lut[0][:3]) == (103, 0, 31) and tuple(lut[255][:3]) == (5, 48, 97)
     img = frame_rgba(np.array([[-1.0, 0.0], [0.5, 1.0]]))
-    assert tuple(img[0, 0][:3]) == (103, 0, 31) and tuple(img[1, 1][:3]) == (5, 48, 97) and img[0, 1][0] > 240
+    # band j takes cmap((j + 0.5) / 99): the outermost bands sit one table entry inside the ends
+    assert np.array_equal(img[0, 0], lut[int(0.5 / 99 * 256)]) and np.array_equal(img[1, 1], lut[int(98.5 / 99 * 256)])
+    assert img[0, 0][0] > 3 * img[0, 0][2] and img[1, 1][2] > 3 * img[1, 1][0] and img[0, 1][:3].min() > 240
     assert (frame_rgba(np.zeros((3, 3))) == frame_rgba(np.zeros((3, 3)))[0, 0]).all()  # abs_max == 0 -> 5: mid band
