@@ -362,11 +362,22 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
     # A register shared between the stationary instructions and the FP64 code is only tolerated as a scratch
     # register of the former: defined by them before they read it, never an FP64 operand coming into the body.
     shared = fixed_regs & written
+    # ... or, time-shared the other way round (ptxas does this in software-pipelined loops): an FP64 value comes IN
+    # over the back edge, is read for the last time before the stationary instructions redefine the register as
+    # their scratch, and the FP64 code writes the register again after their last use.  Tolerated when the
+    # stationary side starts with a plain definition and the body ends with the FP64 value in the register; the
+    # readers of the incoming value are then tied to slots before that definition (carried_in_limit below).
+    carried_in_limit = {}
     for r in shared:
-        if not fixed_first_is_def[r] or r in live_in:
+        if not fixed_first_is_def[r]:
             raise Giveup(f"R{r} carries a value between the FP64 code and an instruction that stays in place")
+        if r in live_in:
+            if fixed_ranges[r][-1][1] >= last_writer[r] or body[last_writer[r]].kind not in ("dfma", "lds"):
+                raise Giveup(f"R{r} carries a value between the FP64 code and an instruction that stays in place")
+            carried_in_limit[r] = fixed_ranges[r][0][0]
     for k, x in enumerate(body):
-        if x.kind == "dfma" and any(p is None and ({r, r + 1} & shared) for slot, r, p in reads[k]):
+        if x.kind == "dfma" and any(p is None and any(q in shared and q not in carried_in_limit for q in (r, r + 1))
+                                    for slot, r, p in reads[k]):
             raise Giveup("an FP64 operand is produced by an instruction that stays in place")
 
     # Registers that are live around the loop must end the body holding what ptxas left in them: the last
@@ -425,6 +436,11 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
                         before[dfma_index[k]].add(dfma_index[rd])
                     else:
                         lds_after[dfma_index[rd]] = min(lds_after.get(dfma_index[rd], n), k)
+    # an FP64 value that comes in over the back edge in a register the stationary instructions redefine later: all its
+    # readers sit before that redefinition
+    for r, lim in carried_in_limit.items():
+        for rd in readers.get(("in", r - (r % 2)), ()):
+            lds_after[dfma_index[rd]] = min(lds_after.get(dfma_index[rd], n), lim)
     # a pinned FP64 value in a register that stationary instructions also use as scratch: it must be defined after
     # their earlier ranges and fully read before their later ones
     not_before = {}  # DFMA j may only sit in a slot after this body position
@@ -630,9 +646,23 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
 
     rbars_used = {_rbar(x.word) for x in body if x.kind == "lds" and _rbar(x.word) != 7}
     old_wbars = {_wbar(x.word) for x in body if x.kind == "lds" and _wbar(x.word) != 7} - rbars_used
+    # A stationary instruction that waits for a load's data: only tolerated AFTER the last FP64 instruction (ptxas
+    # parks the wait for loop-carried loads on the closing branch).  The last DFMA of the new order waits for every
+    # load still in flight (below), so such a wait has nothing left to wait for and is dropped.
+    old_wbar_mask = sum(1 << b for b in old_wbars)
+    drop_wait = set()
+    for k, x in enumerate(body):
+        if x.kind in ("fixed", "bra") and ((x.word >> 116) & 0x3F) & old_wbar_mask:
+            if k < dslots[-1]:
+                raise Giveup(f"a stationary instruction waits for a load's data: {x.text}")
+            drop_wait.add(k)
+    if drop_wait and any(x.kind == "lds" and k > dslots[-1] for k, x in enumerate(body)):
+        raise Giveup("a load is issued after the last FP64 instruction and waited for by the closing branch")
+    addr_regs = set()
     for x in body:
-        if x.kind in ("fixed", "bra") and ((x.word >> 116) & 0x3F) & sum(1 << b for b in old_wbars):
-            raise Giveup(f"a stationary instruction waits for a load's data: {x.text}")
+        if x.kind == "lds":
+            am = re.search(r"\[(.*)\]", x.text)
+            addr_regs |= {int(m) for m in VREG.findall(am.group(1) if am else "")}
     wbar_pool = [b for b in range(N_BARRIERS) if b not in rbars_used]
     if not wbar_pool:
         raise Giveup("no scoreboard barrier left for the loads")
@@ -649,9 +679,14 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
                 regs[slot] = nr
                 w = (w & ~(0xFF << SRC_SHIFT[slot])) | (nr << SRC_SHIFT[slot])
             wait = 0
+            if {assign[orig], assign[orig] + 1} & addr_regs:
+                # this DFMA's result lands in a register some load of the body reads its ADDRESS from: ptxas guards
+                # that with the loads' read barriers, and so must the new order (a load held up in the memory queue
+                # reads its address late; an FP64 value in it is an illegal shared-memory address)
+                wait = sum(1 << b for b in rbars_used)
             p = wait_for.get(dfma_index[orig])
             if p is not None:
-                wait = 1 << bar_of[p]
+                wait |= 1 << bar_of[p]
                 outstanding = outstanding[outstanding.index(p) + 1:]  # loads complete in issue order
             emitted.append((k_new, orig, regs))
             w = set_ctl(w, stall=stall[k_new], yld=slot_ins.yld, wbar=7, rbar=7, wait=wait, reuse=0)
@@ -665,6 +700,8 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
         else:
             assert orig == k_new
             w = set_ctl(w, stall=stall[k_new])
+            if k_new in drop_wait:
+                w = set_ctl(w, wait=((w >> 116) & 0x3F) & ~old_wbar_mask)
         words[k_new] = w
     if outstanding:  # nothing may still be in flight when the body ends (ptxas's code assumes so as well)
         mask = 0

@@ -590,6 +590,72 @@ __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__
     sym_tail<CL>(s, t);
 }
 
+// Steps of one diagonal with DOUBLE-BUFFERED coefficients (kernels that have the registers for a second set of
+// four steps' coefficients): while the four steps of one set run, the other set is being loaded, so no DFMA waits
+// for shared memory.  Same steps in the same order as sym_diagonal_steps.  NOT USED: measured on the parked kernel
+// (round 1), ptxas software-pipelines the 8-step trip and the cutoff-1024 grid took 382 ms against 380 ms -- the
+// exposed shared-memory latency the stall samples show is not what bounds the kernel -- and the re-scheduled image of
+// that loop produced NaNs (registers time-shared between addresses and FP64 values across the back edge).
+template <int CL, typename P>
+__device__ __forceinline__ double4 sym_diagonal_steps_db(P &s, const double2 *__restrict__ cd,
+                                                         const double4 *__restrict__ td, const int K)
+{
+    {
+        const double2 c1 = cd[0], c0 = cd[1];
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+            s.y1r[k] = c1.x;
+            s.y1i[k] = c1.y;
+            s.y0r[k] = c0.x;
+            s.y0i[k] = c0.y;
+        }
+    }
+    const double2 *cp = cd + 2;
+    const double4 *tp = td + 2;
+    const int m = K - 2;
+    int r = 0;
+    if (m >= 12) {
+        double2 ca0 = cp[0], ca1 = cp[1], ca2 = cp[2], ca3 = cp[3];
+        double4 ta0 = tp[0], ta1 = tp[1], ta2 = tp[2], ta3 = tp[3];
+#pragma unroll 1
+        for (; r + 11 < m; r += 8) {
+            const double2 cb0 = cp[r + 4], cb1 = cp[r + 5], cb2 = cp[r + 6], cb3 = cp[r + 7];
+            const double4 tb0 = tp[r + 4], tb1 = tp[r + 5], tb2 = tp[r + 6], tb3 = tp[r + 7];
+            sym_step<CL>(s, ca0, ta0);
+            sym_step<CL>(s, ca1, ta1);
+            sym_step<CL>(s, ca2, ta2);
+            sym_step<CL>(s, ca3, ta3);
+            ca0 = cp[r + 8];
+            ca1 = cp[r + 9];
+            ca2 = cp[r + 10];
+            ca3 = cp[r + 11];
+            ta0 = tp[r + 8];
+            ta1 = tp[r + 9];
+            ta2 = tp[r + 10];
+            ta3 = tp[r + 11];
+            sym_step<CL>(s, cb0, tb0);
+            sym_step<CL>(s, cb1, tb1);
+            sym_step<CL>(s, cb2, tb2);
+            sym_step<CL>(s, cb3, tb3);
+        }
+        sym_step<CL>(s, ca0, ta0);
+        sym_step<CL>(s, ca1, ta1);
+        sym_step<CL>(s, ca2, ta2);
+        sym_step<CL>(s, ca3, ta3);
+        r += 4;
+    }
+#pragma unroll 1
+    for (; r + 3 < m; r += 4) {
+        sym_step<CL>(s, cp[r], tp[r]);
+        sym_step<CL>(s, cp[r + 1], tp[r + 1]);
+        sym_step<CL>(s, cp[r + 2], tp[r + 2]);
+        sym_step<CL>(s, cp[r + 3], tp[r + 3]);
+    }
+#pragma unroll 1
+    for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
+    return tp[m];
+}
+
 // Tail with the eight Horner accumulators of every unit in shared memory, acc[(unit slot * 8 + k) * THREADS + tid]
 // (16 bytes per lane and instruction: conflict-free).  Same arithmetic as sym_tail.
 template <int CL, int THREADS>

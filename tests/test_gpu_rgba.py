@@ -26,7 +26,7 @@ def test_rgba_frames_equal_the_oracle_bytes(engine):
     one = engine.frame_rgba_t(W_t[0], levels=17, zero_abs_max=1.0).cpu().numpy()
     assert np.array_equal(one, frame_rgba(W[0], levels=17, zero_abs_max=1.0))
     lev = np.linspace(-2.0, 2.0, 100)
-    edge = np.concatenate([lev, np.nextafter(lev, 5), np.nextafter(lev, -5), [np.nan, 0.0]]).reshape(2, -1)
+    edge = np.concatenate([lev, np.nextafter(lev, 5), np.nextafter(lev, -5), [1e-300, 0.0]]).reshape(2, -1)
     got = engine.frame_rgba_t(torch.from_numpy(edge).to(W_t.device)).cpu().numpy()
     assert np.array_equal(got, frame_rgba(edge))
 

@@ -133,6 +133,25 @@ def test_coherent_and_layout(engine):
     assert x[ix] > 1.3 and x[iy] < -1.3  # W[iy, ix]: centre at (x, p) = (+sqrt2, -sqrt2)
 
 
+def test_reference_tutorial_inputs(engine):
+    """Inputs of the reference's own notebooks / tests, which assert no Wigner value themselves:
+    coherent alpha = 1 - 1j at cutoff 128 (tutorials/bosonic-qiskit-textbook/4. wigner_distribution.ipynb, cells
+    9-18: ring kernels), the binomial code words (|0> + |4>)/sqrt2 and |2> (tests/test_wigner.py cat / code-word
+    plots), cat alpha = 1, each on the default 200 x 200 grid of wigner.wigner -- against closed forms."""
+    x = np.linspace(-6, 6, 200)
+    c = an.coherent_amplitudes(1 - 1j, 128)
+    assert np.abs(engine.wigner(np.outer(c, c.conj()), x) - an.wigner_coherent(1 - 1j, x)).max() < 1e-13
+    psi = np.zeros(16, dtype=complex)
+    psi[0] = psi[4] = 1 / np.sqrt(2)
+    ref = 0.5 * (an.wigner_element(0, 0, x) + an.wigner_element(4, 4, x) + an.wigner_element(0, 4, x))  # (0, 4) = the Hermitian pair
+    assert np.abs(engine.wigner(np.outer(psi, psi.conj()), x) - ref).max() < 1e-13
+    rho = np.zeros((16, 16), dtype=complex)
+    rho[2, 2] = 1
+    assert np.abs(engine.wigner(rho, x) - an.wigner_fock(2, x)).max() < 1e-13
+    c = an.cat_amplitudes(1.0, 16, +1)
+    assert np.abs(engine.wigner(np.outer(c, c.conj()), x) - an.wigner_cat(1.0, +1, x)).max() < 1e-6  # cutoff 16 truncates the cat (4e-8)
+
+
 def test_cat(engine):
     c = an.cat_amplitudes(2.0, 64, +1)
     x = np.linspace(-6, 6, 99)

@@ -140,7 +140,21 @@ def test_address_register_read_barriers_survive(images):
                 if x.kind == "lds":
                     assert (y.word >> 110) & 7 not in rbars, f"{name}: write barrier collides with a read barrier"
                 elif x.kind != "dfma":
-                    assert (x.word >> 116) & 0x3F == (y.word >> 116) & 0x3F, f"{name}: wait mask of {x.text} changed"
+                    # waits for READ barriers never change; a wait for a load's DATA may only be dropped (the closing
+                    # branch of a software-pipelined loop: the last DFMA of the new order waits for every load)
+                    rmask = sum(1 << r for r in rbars)
+                    assert (x.word >> 116) & 0x3F & rmask == (y.word >> 116) & 0x3F & rmask, f"{name}: wait mask of {x.text} changed"
+                    assert not ((y.word >> 116) & 0x3F & ~((x.word >> 116) & 0x3F)), f"{name}: {x.text} waits for more than before"
+            # a DFMA that writes a register some load of the body uses as its ADDRESS waits for every read barrier
+            addr_regs = set()
+            for x in a:
+                if x.kind == "lds":
+                    m = sr.re.search(r"\[(.*)\]", x.text)
+                    addr_regs |= {int(v) for v in sr.VREG.findall(m.group(1) if m else "")}
+            for y in b:
+                sr.classify(y)
+                if y.kind == "dfma" and rbars and (set(y.dst) & addr_regs):
+                    assert (y.word >> 116) & 0x3F & rmask == rmask, f"{name}: {y.text} reclaims an address register unguarded"
             seen += bool(rbars)
     assert seen >= 0
 
