@@ -1343,6 +1343,33 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 split_tpf = rounds * split_main->ctas / p.batch;
             }
         }
+        // Ring kernels (N > 64), one frame: whole rounds with one variant and the remainder with ANOTHER one when that is
+        // predicted to finish >= 3 % earlier (a rank's share of cutoff 1024 / 4096^2 on 8 GPUs is 1.73 rounds of the
+        // parked 4-unit tile: one such round + one round of the 3-unit tile instead of two).  Variants agree bit for
+        // bit per unit.  Not for the resident kernels: there a round's duration is not proportional to the units per
+        // thread (the measured-and-shelved split above).
+        if (!resident && best && dev.sym_force < 0 && dev.sym_split_main < 0 && p.batch == 1) {
+            double split_cost = best_cost * 0.97;
+            for (int i = 0; i < ncand; ++i) {
+                const Cand &c = cand[i];
+                const int64_t full = c.tiles / c.ctas;
+                if (full < 1 || c.tiles % c.ctas == 0) continue;
+                const int64_t m = full * c.ctas * c.v->threads * c.v->cl;
+                if (m >= p.sym_units) continue;
+                const int64_t tail = p.sym_units - m;
+                for (int j = 0; j < ncand; ++j) {
+                    const Cand &u = cand[j];
+                    const int64_t tiles_u = ((tail + u.v->cl - 1) / u.v->cl + u.v->threads - 1) / u.v->threads;
+                    const double cost = (double)full * c.round_cost + (double)((tiles_u + u.ctas - 1) / u.ctas) * u.round_cost;
+                    if (cost < split_cost) {
+                        split_cost = cost;
+                        split_main = &c;
+                        split_tail = &u;
+                        split_tpf = full * c.ctas;
+                    }
+                }
+            }
+        }
         if (split_main && split_tail && split_tpf > 0) {
             const int64_t m = std::min<int64_t>(split_tpf * split_main->v->threads * split_main->v->cl, p.sym_units);
             cudaError_t e = launch_range(*split_main->v, p.sym_first, m);
