@@ -246,6 +246,8 @@ def run_reference(args, rank: int, world: int):
     ms = 1e3 * float(np.mean(times))
     value = rows * S / (ms * 1e-3)
     sample = f"{rows} of {S} grid rows x {S} columns per step, {procs} worker processes (rows split evenly)"
+    # same `scaling` label as the B200 arm of this configuration (config 5 on N > 1 GPUs is one grid: strong)
+    one_grid = world > 1 and args.config == "c5" and args.sharding in ("auto", "grid")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if one_grid else "weak", "vs_baseline": None,

@@ -85,3 +85,31 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "oracle/" not in text and "liboracle" not in text, f
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` needs no GPU: it must run here, print exactly one JSON line with the contract's
+    keys, and (under torchrun) only on rank 0."""
+    import json
+    import subprocess
+    import sys
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1", "--steps", "1", "--warmup", "1",
+           "--cpu-seconds", "1"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    res = subprocess.run(cmd + ["--gpus", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert res.returncode == 0 and res.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    res = subprocess.run(cmd[:4] + ["--config", "c5", "--steps", "1", "--warmup", "1", "--cpu-seconds", "1", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert json.loads(res.stdout.strip())["scaling"] == "strong"
