@@ -8,7 +8,8 @@ reference's own.  All arithmetic runs in hand-written sm_100a CUDA kernels behin
 
 from . import animate, util, wigner  # noqa: F401
 from ._lib import BQError  # noqa: F401
-from .engine import Engine, get_engine  # noqa: F401
+from .engine import Engine, MultiEngine, device_count, get_engine, get_multi_engine  # noqa: F401
 
-__version__ = "0.1.0"
-__all__ = ["wigner", "util", "animate", "Engine", "get_engine", "BQError", "__version__"]
+__version__ = "0.2.0"
+__all__ = ["wigner", "util", "animate", "Engine", "MultiEngine", "get_engine", "get_multi_engine", "device_count", "BQError",
+           "__version__"]

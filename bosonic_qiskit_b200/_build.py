@@ -20,12 +20,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 GEN = os.path.join(CSRC, "_gen")
 LIB_PATH = os.path.join(_HERE, "libbq_b200.so")
-SOURCES = ["bq_api.cu", "wigner_kernels.cu", "ptrace_kernels.cu", "wigner_fft_kernels.cu"]
+SOURCES = ["bq_api.cu", "bq_multi.cu", "wigner_kernels.cu", "ptrace_kernels.cu", "wigner_fft_kernels.cu"]
 HEADERS = ["bq_common.cuh", "bq_internal.h", os.path.join("..", "..", "include", "bq_b200.h"),
            os.path.join("..", "_sass_resched.py"), os.path.join("..", "_build.py")]
 
 ARCH_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"]
-NVCC_FLAGS = [*ARCH_FLAGS, "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = [*ARCH_FLAGS, "-Xcompiler", "-fPIC,-pthread", "-shared"]
 MAX_REGS = 128  # the resident kernels' __launch_bounds__ (2 x 256 or 4 x 128 threads per SM) allow 128 registers
 # the streaming kernels run one CTA per SM (their __launch_bounds__ say so): room for the re-scheduler's temporaries
 MAX_REGS_FOR = [("wigner_stream_kernelILi4ELi256", 168), ("wigner_stream_kernelILi2ELi128", 168),
@@ -61,6 +61,20 @@ def _run(cmd, cwd):
     return res.stdout + res.stderr
 
 
+# The re-scheduler decodes the control words ptxas of THESE releases emits for sm_100a; under any other toolchain the
+# build ships nvcc's own schedule (override: BQ_B200_FORCE_PATCH=1).  The library additionally compares every patched
+# kernel with its nvcc-scheduled twin bit for bit when it is loaded (bq_sass_self_check).
+PATCH_TOOLCHAINS = ("12.9.86",)
+
+
+def nvcc_release() -> str:
+    out = _run([_nvcc(), "--version"], CSRC)
+    for tok in out.replace(",", " ").split():
+        if tok.startswith("V") and tok[1:2].isdigit():
+            return tok[1:]
+    return "unknown"
+
+
 def build_patched_image(verbose: bool = False) -> bool:
     """Steps 1-3.  Returns True when ``_gen/wigner_cubin.inc`` holds a re-scheduled image."""
     from . import _sass_resched
@@ -69,11 +83,18 @@ def build_patched_image(verbose: bool = False) -> bool:
     cubin = os.path.join(GEN, "wigner_kernels.cubin")
     patched = os.path.join(GEN, "wigner_kernels.patched.cubin")
     _run([_nvcc(), *ARCH_FLAGS, "-cubin", "-o", cubin, "wigner_kernels.cu"], CSRC)
-    try:
-        report = _sass_resched.patch_file(cubin, patched, min_dfma=20, max_regs=MAX_REGS, max_regs_for=MAX_REGS_FOR)
-    except Exception as exc:  # the tool refuses rather than guesses; a refusal must not break the build
-        report = [f"re-scheduler failed: {exc!r}"]
+    release = nvcc_release()
+    if release not in PATCH_TOOLCHAINS and os.environ.get("BQ_B200_FORCE_PATCH") != "1":
+        report = [f"nvcc {release} is not a toolchain the re-scheduler was validated with {PATCH_TOOLCHAINS}: "
+                  "shipping nvcc's own schedule"]
         shutil.copyfile(cubin, patched)
+    else:
+        try:
+            report = [f"nvcc {release}"] + _sass_resched.patch_file(cubin, patched, min_dfma=20, max_regs=MAX_REGS,
+                                                                    max_regs_for=MAX_REGS_FOR)
+        except Exception as exc:  # the tool refuses rather than guesses; the refusal is in the report, and
+            report = [f"re-scheduler failed: {exc!r}"]  # tests/test_sass_resched.py fails on it
+            shutil.copyfile(cubin, patched)
     with open(os.path.join(GEN, "sass_resched_report.txt"), "w") as f:
         f.write("\n".join(report) + "\n")
     if verbose:

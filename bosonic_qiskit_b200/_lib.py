@@ -32,6 +32,9 @@ SIGNATURES = {
     "bq_partial_trace_sv_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_void_p]),
     "bq_partial_trace_sv_multi_host": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_void_p]),
     "bq_partial_trace_sv_multi_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_void_p, c_void_p]),
+    "bq_partial_trace_sv_accumulate_host": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_void_p]),
+    "bq_partial_trace_sv_accumulate_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_void_p,
+                                                   c_void_p]),
     "bq_partial_trace_dm_host": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_void_p]),
     "bq_partial_trace_dm_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_void_p, c_void_p]),
     "bq_photon_number_host": (c_int, [_H, c_void_p, c_int, c_int, c_void_p]),
@@ -48,6 +51,10 @@ SIGNATURES = {
                                         c_int, c_double, c_int, c_void_p, c_void_p]),
     "bq_state_to_wigner_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,
                                        c_int, c_double, c_int, c_void_p, c_void_p, c_void_p]),
+    "bq_state_to_wigner_multi_host": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                              c_double, c_int, c_void_p, c_void_p]),
+    "bq_state_to_wigner_multi_dev": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+                                             c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "bq_frame_minmax_dev": (c_int, [_H, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "bq_frame_rgba_dev": (c_int, [_H, c_void_p, c_int64, c_int, c_int, c_double, c_void_p, c_void_p]),
     "bq_rdbu_lut": (c_int, [c_void_p]),
@@ -55,6 +62,7 @@ SIGNATURES = {
     "bq_last_device_ms": (c_int, [_H, _dp]),
     "bq_profile_enable": (c_int, [_H, c_int]),
     "bq_set_sass_mode": (c_int, [_H, c_int, _ip]),
+    "bq_sass_self_check": (c_int, [_H, POINTER(c_uint64), _ip]),
     "bq_profile_read": (c_int, [_H, _dp, _ip]),
     "bq_set_grid_symmetry": (c_int, [_H, c_int]),
     "bq_set_unit_range": (c_int, [_H, c_int64, c_int64]),
@@ -62,6 +70,15 @@ SIGNATURES = {
     "bq_set_sym_variant": (c_int, [_H, c_int]),
     "bq_last_wigner_variant": (c_int, [_H, _ip]),
     "bq_grid_is_mirror": (c_int, [c_void_p, c_int, c_void_p, c_int]),
+    "bq_multi_init": (c_int, [POINTER(_H), c_int, _ip]),
+    "bq_multi_finalize": (c_int, [_H]),
+    "bq_multi_device_count": (c_int, [_H, _ip]),
+    "bq_multi_handle": (c_int, [_H, c_int, POINTER(_H)]),
+    "bq_multi_launch_count": (c_int, [_H, POINTER(c_uint64)]),
+    "bq_state_to_wigner_sharded_host": (c_int, [_H, c_void_p, c_int, _ip, c_int, c_int, c_int64, c_void_p, c_int, c_void_p,
+                                                c_int, c_double, c_int, c_int, c_void_p, c_void_p]),
+    "bq_wigner_sharded_host": (c_int, [_H, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p, c_int,
+                                       c_double, c_int, c_int, c_void_p]),
     "bq_device_alloc": (c_int, [_H, c_size_t, POINTER(c_void_p)]),
     "bq_device_free": (c_int, [_H, c_void_p]),
     "bq_ipc_export": (c_int, [_H, c_void_p, c_void_p]),
@@ -71,6 +88,7 @@ SIGNATURES = {
 }
 
 BQ_OK, BQ_ERR_INVALID, BQ_ERR_CUDA, BQ_ERR_NO_DEVICE, BQ_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+BQ_SHARD_FRAMES, BQ_SHARD_GRID = 0, 1
 
 _lib = None
 

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in Nsight Systems / ncu --nvtx, cost nothing otherwise
+
 #include "../../include/bq_b200.h"
 #include "bq_internal.h"
 
@@ -32,6 +34,11 @@ int fail_cuda(cudaError_t e, const char *what)
         cudaError_t e__ = (call);                      \
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
+
+struct NvtxRange {  // one range per public call around its enqueues (K1 / K3 / K4 launches and copies)
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Buffer {  // grow-only device scratch
     void *ptr = nullptr;
@@ -88,6 +95,8 @@ struct bq_handle_s {
     uint64_t launches = 0;
     double last_ms = 0.0;
     bool profile = false;
+    int sass_checked = 0;  // kernel variants the load-time SASS self-check compared on this device
+    bool fused = true;  // the Wigner launch builds its coefficient stream in its own prologue (BQ_B200_FUSED=0: separate launches)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
@@ -208,10 +217,22 @@ int check_method(int method)
     }
 }
 
-// device-side core: rho (device) -> W (device)
-int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
-                const double *d_x, int nx, const double *d_y, int ny, double g, double *d_W, cudaStream_t st,
-                bool mirror_grid)
+// Where the Wigner kernel's coefficient stream comes from: density matrices, or statevectors that the kernel's fused
+// prologue traces itself (csrc/wigner_kernels.cu, fused_prologue).
+struct WigSource {
+    const double2 *rho = nullptr;  // [batch][N][ld]
+    int64_t ld = 0, rho_stride = 0;
+    const double2 *psi = nullptr;  // psi_batch statevectors; frame f = set * psi_batch + b
+    int64_t psi_stride = 0;
+    int psi_batch = 0;
+    const bq::TraceMap *maps = nullptr;
+    int n_keep = 0, n_trace = 0;
+    double2 *rho_out = nullptr;  // optional, [batch][N][N]
+};
+
+// device-side core: rho or psi (device) -> W (device)
+int wigner_core(bq_handle_t h, const WigSource &src, int N, int batch, const double *d_x, int nx, const double *d_y, int ny,
+                double g, double *d_W, cudaStream_t st, bool mirror_grid)
 {
     if (batch == 0 || nx == 0 || ny == 0) return BQ_OK;
     const double4 *tab = nullptr;
@@ -220,15 +241,32 @@ int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t 
     const int64_t R = bq::stream_records(N);
     CU(h->cs.reserve((size_t)R * batch * sizeof(double2)));
     int nl = 0;
-    for (int b0 = 0; b0 < batch; b0 += 65535) {
-        const int nb = std::min(65535, batch - b0);
-        cudaError_t e = bq::launch_pack_rho(d_rho + (int64_t)b0 * rho_stride, ld, rho_stride, N, nb,
-                                            (double2 *)h->cs.ptr + (int64_t)b0 * R, R, st);
-        if (e != cudaSuccess) return fail_cuda(e, "pack_rho");
-        ++nl;
-    }
     bq::WigParams p{};
     p.cs = (const double2 *)h->cs.ptr;
+    p.cs_w = (double2 *)h->cs.ptr;
+    if (src.psi) {
+        p.pro_mode = 2;
+        p.pro_psi = src.psi;
+        p.pro_psi_stride = src.psi_stride;
+        p.pro_psi_batch = src.psi_batch;
+        p.pro_maps = src.maps;
+        p.pro_n_keep = src.n_keep;
+        p.pro_n_trace = src.n_trace;
+        p.pro_rho_out = src.rho_out;
+    } else if (h->fused) {
+        p.pro_mode = 1;
+        p.pro_rho = src.rho;
+        p.pro_ld = src.ld;
+        p.pro_rho_stride = src.rho_stride;
+    } else {
+        for (int b0 = 0; b0 < batch; b0 += 65535) {
+            const int nb = std::min(65535, batch - b0);
+            cudaError_t e = bq::launch_pack_rho(src.rho + (int64_t)b0 * src.rho_stride, src.ld, src.rho_stride, N, nb,
+                                                (double2 *)h->cs.ptr + (int64_t)b0 * R, R, st);
+            if (e != cudaSuccess) return fail_cuda(e, "pack_rho");
+            ++nl;
+        }
+    }
     p.tab = tab;
     p.xvec = d_x;
     p.yvec = d_y;
@@ -247,7 +285,7 @@ int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t 
     p.sym_want_count = h->unit_count;
     if (h->unit_count >= 0 && !p.sym)
         return fail(BQ_ERR_UNSUPPORTED, "a unit range needs a mirror-symmetric grid (bq_set_grid_symmetry / bq_grid_is_mirror)");
-    p.ctr = h->ctr + 2 * h->ctr_next;
+    p.ctr = h->ctr + 4 * h->ctr_next;
     h->ctr_next = (h->ctr_next + 1) % kCtrSlots;
     cudaEvent_t pa = nullptr, pb = nullptr;
     if (h->profile) {
@@ -267,6 +305,17 @@ int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t 
     }
     if (e != cudaSuccess) return fail_cuda(e, "launch_wigner");
     return BQ_OK;
+}
+
+int wigner_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                const double *d_x, int nx, const double *d_y, int ny, double g, double *d_W, cudaStream_t st,
+                bool mirror_grid)
+{
+    WigSource src;
+    src.rho = d_rho;
+    src.ld = ld;
+    src.rho_stride = rho_stride;
+    return wigner_core(h, src, N, batch, d_x, nx, d_y, ny, g, d_W, st, mirror_grid);
 }
 
 int check_wigner_args(const void *rho, int N, int64_t ld, int64_t rho_stride, int batch, const void *x, int nx,
@@ -387,6 +436,9 @@ struct HostTimer {
 
 }  // namespace
 
+// lets the other translation units of the library (bq_multi.cu) set the calling thread's bq_last_error()
+extern "C" __attribute__((visibility("hidden"))) int bq_internal_fail(int code, const char *msg) { return fail(code, msg ? msg : ""); }
+
 extern "C" {
 
 int bq_version(void) { return BQ_B200_VERSION; }
@@ -431,8 +483,36 @@ int bq_create(bq_handle_t *out, int device)
         const char *sv = std::getenv("BQ_B200_SYM_VARIANT");
         h->dev.sym_force = sv ? std::atoi(sv) : -1;
         if (const char *sp = std::getenv("BQ_B200_SYM_SPLIT")) std::sscanf(sp, "%d:%d", &h->dev.sym_split_main, &h->dev.sym_split_tail);
+        const char *fu = std::getenv("BQ_B200_FUSED");
+        h->fused = !(fu && fu[0] == '0');
         const char *env = std::getenv("BQ_B200_SASS");
         h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
+    }
+    if (bq::patched_sass_available()) {
+        // load-time self-check of the re-scheduled SASS, once per device and process (BQ_B200_SASS_VERIFY=0 skips it)
+        static std::mutex vmu;
+        static std::map<int, std::pair<uint64_t, int>> verdicts;
+        std::lock_guard<std::mutex> vlk(vmu);
+        auto it = verdicts.find(device);
+        if (it == verdicts.end()) {
+            uint64_t bad = 0;
+            int checked = 0;
+            const char *vf = std::getenv("BQ_B200_SASS_VERIFY");
+            if (!(vf && vf[0] == '0')) {
+                cudaError_t ve = bq::verify_patched_kernels(h->dev, &bad, &checked);
+                if (ve != cudaSuccess) {
+                    cudaGetLastError();
+                    bad = ~0ull;  // could not compare: nvcc's schedule for everything
+                    std::fprintf(stderr, "libbq_b200: SASS self-check could not run (%s); using nvcc's schedule\n", cudaGetErrorString(ve));
+                } else if (bad) {
+                    std::fprintf(stderr, "libbq_b200: re-scheduled SASS of kernel variants 0x%llx differs from nvcc's schedule; "
+                                         "those variants run nvcc's schedule\n", (unsigned long long)bad);
+                }
+            }
+            it = verdicts.emplace(device, std::make_pair(bad, checked)).first;
+        }
+        h->dev.patched_bad = it->second.first;
+        h->sass_checked = it->second.second;
     }
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -443,8 +523,8 @@ int bq_create(bq_handle_t *out, int device)
               cudaEventCreateWithFlags(&h->ev_block[3], cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_order, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&h->ev_t0) == cudaSuccess && cudaEventCreate(&h->ev_t1) == cudaSuccess &&
-              cudaMalloc(&h->ctr, sizeof(unsigned int) * 2 * kCtrSlots) == cudaSuccess &&
-              cudaMemset(h->ctr, 0, sizeof(unsigned int) * 2 * kCtrSlots) == cudaSuccess;
+              cudaMalloc(&h->ctr, sizeof(unsigned int) * 4 * kCtrSlots) == cudaSuccess &&
+              cudaMemset(h->ctr, 0, sizeof(unsigned int) * 4 * kCtrSlots) == cudaSuccess;
     if (!ok) {
         cudaError_t le = cudaGetLastError();
         bq_destroy(h);
@@ -594,6 +674,68 @@ int bq_partial_trace_sv_multi_host(bq_handle_t h, const double *psi, int n_qubit
     if (n_sets < 0 || n_sets > 4096) return fail(BQ_ERR_INVALID, "n_sets out of range [0, 4096]");
     if (n_sets == 0) return BQ_OK;
     return trace_sv_host_common(h, psi, n_qubits, traced, n_traced, n_sets, 1, 0, rho_out);
+}
+
+// ---- shot-averaged partial trace ---------------------------------------------------------------
+static int trace_accumulate_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced, int shots,
+                                 int64_t psi_stride, const double *d_weights, double2 *d_rho, cudaStream_t st)
+{
+    const bq::TraceMap *maps = nullptr;
+    int rc = get_maps(h, n_qubits, traced, n_traced, 1, &maps);
+    if (rc) return rc;
+    const int n_keep = n_qubits - n_traced;
+    if (n_keep > 15) return fail(BQ_ERR_INVALID, "reduced density matrix larger than 2^15 x 2^15");
+    if (shots > 65535) return fail(BQ_ERR_INVALID, "more than 65535 shots in one call");
+    CU(h->partial.reserve(bq::trace_sv_scratch_bytes(n_keep, n_traced, shots, 1)));
+    int nl = 0;
+    cudaError_t e = bq::launch_trace_sv_accumulate(d_psi, psi_stride, shots, maps, 1, n_keep, n_traced, d_weights, d_rho,
+                                                   (double2 *)h->partial.ptr, h->dev, st, &nl);
+    h->launches += nl;
+    if (e != cudaSuccess) return fail_cuda(e, "launch_trace_sv_accumulate");
+    return BQ_OK;
+}
+
+int bq_partial_trace_sv_accumulate_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                                       int shots, int64_t psi_stride, const double *d_weights, double *d_rho_out,
+                                       void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_trace_args(d_psi, n_qubits, n_traced, shots, psi_stride, d_rho_out);
+    if (rc) return rc;
+    if (shots == 0) return fail(BQ_ERR_INVALID, "the average of zero shots is undefined");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    NvtxRange range("bq_partial_trace_sv_accumulate_dev");
+    return trace_accumulate_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, shots, psi_stride, d_weights,
+                                 (double2 *)d_rho_out, st);
+}
+
+int bq_partial_trace_sv_accumulate_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                        int shots, int64_t psi_stride, const double *weights, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_trace_args(psi, n_qubits, n_traced, shots, psi_stride, rho_out);
+    if (rc) return rc;
+    if (shots == 0) return fail(BQ_ERR_INVALID, "the average of zero shots is undefined");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    if ((rc = order_stream(h, h->stream))) return rc;
+    const int64_t dim = (int64_t)1 << n_qubits, D = (int64_t)1 << (n_qubits - n_traced);
+    const size_t in_elems = (size_t)((int64_t)(shots - 1) * psi_stride + dim);
+    CU(h->in_dev.reserve(in_elems * sizeof(double2)));
+    CU(h->rho_dev.reserve((size_t)D * D * sizeof(double2)));
+    if (weights) CU(h->small_dev.reserve((size_t)shots * sizeof(double)));
+    NvtxRange range("bq_partial_trace_sv_accumulate_host");
+    HostTimer timer(h);
+    CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    if (weights) CU(cudaMemcpyAsync(h->small_dev.ptr, weights, (size_t)shots * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = trace_accumulate_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, shots, psi_stride,
+                               weights ? (const double *)h->small_dev.ptr : nullptr, (double2 *)h->rho_dev.ptr, h->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, (size_t)D * D * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    return timer.finish();
 }
 
 static int trace_dm_core(bq_handle_t h, const double2 *d_rho, int n_qubits, const int *traced, int n_traced, int batch,
@@ -835,21 +977,47 @@ int bq_wigner_fft_host(bq_handle_t h, const double *rho, int N, int64_t ld, int6
 }
 
 // ---- fused frame loop --------------------------------------------------------------------------
+// psi -> (rho) -> W for n_sets traces of each of psi_batch statevectors (frame f = set * psi_batch + b).  Small traces
+// are done by the Wigner launch itself (fused prologue, one launch per call); large ones by the DMMA kernel first.
+static bool trace_fits_prologue(const bq_handle_t h, int n_keep, int n_traced, int64_t frames)
+{
+    if (!h->fused || n_keep > 12) return false;
+    const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_traced;
+    const int64_t items = frames * (D * (D + 1) / 2);
+    // serial length of the prologue per warp (thread) on a conservatively small grid of 512 warps
+    const int64_t est = T < 32 ? ((items + 16383) / 16384) * T : ((items + 511) / 512) * (T / 32);
+    return est <= 256;
+}
+
 static int state_to_wigner_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced,
-                                int batch, int64_t psi_stride, const double *dx, int nx, const double *dy, int ny,
-                                double g, double *d_W, double2 *d_rho_opt, cudaStream_t st, bool mirror_grid)
+                                int n_sets, int batch, int64_t psi_stride, const double *dx, int nx, const double *dy,
+                                int ny, double g, double *d_W, double2 *d_rho_opt, cudaStream_t st, bool mirror_grid)
 {
     const int n_keep = n_qubits - n_traced;
     if (n_keep > 14) return fail(BQ_ERR_INVALID, "reduced density matrix larger than 2^14 x 2^14");
     const int64_t D = (int64_t)1 << n_keep;
+    const int64_t frames = (int64_t)batch * n_sets;
+    if (frames > 0x7fffffffLL) return fail(BQ_ERR_INVALID, "too many frames");
+    if (trace_fits_prologue(h, n_keep, n_traced, frames)) {
+        WigSource src;
+        int rc = get_maps(h, n_qubits, traced, n_traced, n_sets, &src.maps);
+        if (rc) return rc;
+        src.psi = d_psi;
+        src.psi_stride = psi_stride;
+        src.psi_batch = batch;
+        src.n_keep = n_keep;
+        src.n_trace = n_traced;
+        src.rho_out = d_rho_opt;
+        return wigner_core(h, src, (int)D, (int)frames, dx, nx, dy, ny, g, d_W, st, mirror_grid);
+    }
     double2 *d_rho = d_rho_opt;
     if (!d_rho) {
-        CU(h->rho_tmp.reserve((size_t)batch * D * D * sizeof(double2)));
+        CU(h->rho_tmp.reserve((size_t)frames * D * D * sizeof(double2)));
         d_rho = (double2 *)h->rho_tmp.ptr;
     }
-    int rc = trace_sv_core(h, d_psi, n_qubits, traced, n_traced, 1, batch, psi_stride, d_rho, st);
+    int rc = trace_sv_core(h, d_psi, n_qubits, traced, n_traced, n_sets, batch, psi_stride, d_rho, st);
     if (rc) return rc;
-    return wigner_core(h, d_rho, (int)D, D, D * D, batch, dx, nx, dy, ny, g, d_W, st, mirror_grid);
+    return wigner_core(h, d_rho, (int)D, D, D * D, (int)frames, dx, nx, dy, ny, g, d_W, st, mirror_grid);
 }
 
 int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
@@ -868,31 +1036,32 @@ int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, con
     DeviceGuard guard(h->dev.device);
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = order_stream(h, st))) return rc;
-    return state_to_wigner_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, batch, psi_stride, d_xvec, nx,
+    return state_to_wigner_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, 1, batch, psi_stride, d_xvec, nx,
                                 d_yvec, ny, g, d_W_out, (double2 *)d_rho_out, st, h->grid_mode == 2);
 }
 
-int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
-                            int batch, int64_t psi_stride, const double *xvec, int nx, const double *yvec,
-                            int ny, double g, int method, double *W_out, double *rho_out)
+// host pointers in, host pointers out; n_sets traces of each statevector (n_sets > 1 only with batch == 1)
+static int state_to_wigner_host_impl(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                     int n_sets, int batch, int64_t psi_stride, const double *xvec, int nx,
+                                     const double *yvec, int ny, double g, int method, double *W_out, double *rho_out)
 {
-    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
     int rc = check_method(method);
     if (rc) return rc;
     if ((rc = check_trace_args(psi, n_qubits, n_traced, batch, psi_stride, W_out))) return rc;
     if (nx < 0 || ny < 0) return fail(BQ_ERR_INVALID, "negative size");
     if (batch > 0 && nx > 0 && ny > 0 && (!xvec || !yvec)) return fail(BQ_ERR_INVALID, "NULL pointer");
     if (!std::isfinite(g)) return fail(BQ_ERR_INVALID, "g is not finite");
-    if (batch == 0) return BQ_OK;
+    if (batch == 0 || n_sets == 0) return BQ_OK;
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->dev.device);
     if ((rc = order_stream(h, h->stream))) return rc;
     const double *dx, *dy;
     if ((rc = stage_grid(h, xvec, nx, yvec, ny, &dx, &dy))) return rc;
     const int64_t dim = (int64_t)1 << n_qubits, D = (int64_t)1 << (n_qubits - n_traced);
+    const int64_t frames = (int64_t)batch * n_sets;
     const size_t in_elems = (size_t)((int64_t)(batch - 1) * psi_stride + dim);
-    const size_t out_b = (size_t)batch * nx * ny * sizeof(double);
-    const size_t rho_b = (size_t)batch * D * D * sizeof(double2);
+    const size_t out_b = (size_t)frames * nx * ny * sizeof(double);
+    const size_t rho_b = (size_t)frames * D * D * sizeof(double2);
     CU(h->in_dev.reserve(in_elems * sizeof(double2)));
     const bool mirror = h->grid_mode >= 1 && h->grid_host_mirror;
     double *d_out = (out_b && !mirror) ? mapped_alias(W_out) : nullptr;
@@ -901,27 +1070,27 @@ int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, cons
         CU(h->out_dev.reserve(std::max<size_t>(out_b, 8)));
         d_out = (double *)h->out_dev.ptr;
     }
-    CU(h->rho_dev.reserve(rho_b));
+    if (rho_out) CU(h->rho_dev.reserve(rho_b));
+    double2 *d_rho = rho_out ? (double2 *)h->rho_dev.ptr : nullptr;
+    NvtxRange range("bq_state_to_wigner_host");
     HostTimer timer(h);
     CU(cudaMemcpyAsync(h->in_dev.ptr, psi, in_elems * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
     // Many frames, staged output (symmetric-grid kernels): the frames go in up to 4 blocks and a finished block's
     // device -> host copy runs on a second stream under the next block's kernel -- the copy (PCIe) is the longer leg
     // of such a call, so what is hidden is the compute.  Blocks keep >= 2 whole rounds of resident CTAs each.
     int blocks = 1;
-    if (!direct && out_b >= ((size_t)8 << 20) && batch >= 8 && nx == ny) {
+    if (!direct && n_sets == 1 && out_b >= ((size_t)8 << 20) && batch >= 8 && nx == ny) {
         const int64_t U = (nx + 1) / 2, units = (int64_t)batch * U * (U + 1) / 2;
         const int64_t round = (int64_t)h->dev.sm_count * 768;  // units one round of the 3-unit tile covers
         blocks = (int)std::max<int64_t>(1, std::min<int64_t>({4, units / (2 * round), (int64_t)batch / 2}));
     }
     if (blocks > 1 && n_qubits - n_traced <= 14) {
         const int64_t frame_pts = (int64_t)nx * ny;
-        rc = trace_sv_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, 1, batch, psi_stride,
-                           (double2 *)h->rho_dev.ptr, h->stream);
-        if (rc) return rc;
         for (int k = 0; k < blocks; ++k) {
             const int b0 = (int)((int64_t)batch * k / blocks), b1 = (int)((int64_t)batch * (k + 1) / blocks);
-            rc = wigner_core(h, (const double2 *)h->rho_dev.ptr + (int64_t)b0 * D * D, (int)D, D, D * D, b1 - b0, dx, nx, dy, ny,
-                             g, d_out + b0 * frame_pts, h->stream, mirror);
+            rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr + (int64_t)b0 * psi_stride, n_qubits, traced, n_traced, 1,
+                                      b1 - b0, psi_stride, dx, nx, dy, ny, g, d_out + b0 * frame_pts,
+                                      d_rho ? d_rho + (int64_t)b0 * D * D : nullptr, h->stream, mirror);
             if (rc) return rc;
             CU(cudaEventRecord(h->ev_block[k], h->stream));
             CU(cudaStreamWaitEvent(h->copy_stream, h->ev_block[k], 0));
@@ -933,12 +1102,53 @@ int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, cons
         CU(cudaStreamWaitEvent(h->stream, h->ev_copied, 0));
         return timer.finish();
     }
-    rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, batch, psi_stride, dx, nx,
-                              dy, ny, g, d_out, (double2 *)h->rho_dev.ptr, h->stream, mirror);
+    rc = state_to_wigner_core(h, (const double2 *)h->in_dev.ptr, n_qubits, traced, n_traced, n_sets, batch, psi_stride, dx, nx,
+                              dy, ny, g, d_out, d_rho, h->stream, mirror);
     if (rc) return rc;
     if (rho_out) CU(cudaMemcpyAsync(rho_out, h->rho_dev.ptr, rho_b, cudaMemcpyDeviceToHost, h->stream));
     if (out_b && !direct) CU(cudaMemcpyAsync(W_out, h->out_dev.ptr, out_b, cudaMemcpyDeviceToHost, h->stream));
     return timer.finish();
+}
+
+int bq_state_to_wigner_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                            int batch, int64_t psi_stride, const double *xvec, int nx, const double *yvec,
+                            int ny, double g, int method, double *W_out, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    return state_to_wigner_host_impl(h, psi, n_qubits, traced, n_traced, 1, batch, psi_stride, xvec, nx, yvec, ny, g, method,
+                                     W_out, rho_out);
+}
+
+int bq_state_to_wigner_multi_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                  int n_sets, const double *xvec, int nx, const double *yvec, int ny, double g,
+                                  int method, double *W_out, double *rho_out)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (n_sets < 0 || n_sets > 4096) return fail(BQ_ERR_INVALID, "n_sets out of range [0, 4096]");
+    return state_to_wigner_host_impl(h, psi, n_qubits, traced, n_traced, n_sets, 1, 0, xvec, nx, yvec, ny, g, method, W_out,
+                                     rho_out);
+}
+
+int bq_state_to_wigner_multi_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                                 int n_sets, const double *d_xvec, int nx, const double *d_yvec, int ny, double g,
+                                 int method, double *d_W_out, double *d_rho_out, void *stream)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    int rc = check_method(method);
+    if (rc) return rc;
+    if ((rc = check_trace_args(d_psi, n_qubits, n_traced, 1, 0, d_W_out))) return rc;
+    if (n_sets < 0 || n_sets > 4096) return fail(BQ_ERR_INVALID, "n_sets out of range [0, 4096]");
+    if (nx < 0 || ny < 0) return fail(BQ_ERR_INVALID, "negative size");
+    if (n_sets > 0 && nx > 0 && ny > 0 && (!d_xvec || !d_yvec)) return fail(BQ_ERR_INVALID, "NULL pointer");
+    if (!std::isfinite(g)) return fail(BQ_ERR_INVALID, "g is not finite");
+    if (n_sets == 0) return BQ_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard guard(h->dev.device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = order_stream(h, st))) return rc;
+    NvtxRange range("bq_state_to_wigner_multi_dev");
+    return state_to_wigner_core(h, (const double2 *)d_psi, n_qubits, traced, n_traced, n_sets, 1, 0, d_xvec, nx, d_yvec, ny, g,
+                                d_W_out, (double2 *)d_rho_out, st, h->grid_mode == 2);
 }
 
 int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, double *d_out,
@@ -1077,6 +1287,8 @@ int bq_memcpy_dev(bq_handle_t h, void *d_dst, const void *d_src, size_t bytes, v
     if (!d_dst || !d_src) return fail(BQ_ERR_INVALID, "NULL pointer");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->dev.device);
+    int rc = order_stream(h, (cudaStream_t)stream);  // the source is usually this handle's own output of a moment ago
+    if (rc) return rc;
     CU(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return BQ_OK;
 }
@@ -1135,6 +1347,14 @@ int bq_set_sass_mode(bq_handle_t h, int mode, int *active)
     DeviceGuard guard(h->dev.device);
     h->dev.sass_mode = (mode == 1 && bq::patched_sass_available()) ? 1 : 0;
     if (active) *active = h->dev.sass_mode;
+    return BQ_OK;
+}
+
+int bq_sass_self_check(bq_handle_t h, uint64_t *bad_mask, int *checked)
+{
+    if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    if (bad_mask) *bad_mask = h->dev.patched_bad;
+    if (checked) *checked = h->sass_checked;
     return BQ_OK;
 }
 

@@ -25,9 +25,17 @@ struct DeviceInfo {
     int sym_split_main = -1, sym_split_tail = -1;  // tuning aid (env BQ_B200_SYM_SPLIT=main:tail): whole rounds / remainder
     int last_variant = -1;  // variant id (kKernelNames index) of the last Wigner kernel launched
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
+    uint64_t patched_bad = 0;  // bit v: the patched image of variant v failed the load-time self-check -> nvcc's schedule
     bool configured[kKernelSlots] = {};
     int occ[kKernelSlots] = {};
     size_t occ_smem[kKernelSlots] = {};
+};
+
+struct TraceMap {
+    // bit positions (ascending significance) of kept and traced qubits in the statevector index
+    int keep[kMaxQubits];
+    int trace[kMaxQubits];
+    int n_keep, n_trace;
 };
 
 struct WigParams {
@@ -39,7 +47,21 @@ struct WigParams {
     int N, R_tot, nx, ny, batch;
     int chunks_per_row, tiles_per_frame, total_tiles, grab, vec_ok;
     double g, scale;
-    unsigned int *ctr;  // [0] next tile, [1] CTAs that left
+    unsigned int *ctr;  // [0] next tile, [1] CTAs that left, [2] CTAs that finished the fused prologue
+    // Fused prologue (one launch per step instead of trace + split reduce + pack + Wigner): before any tile is
+    // started the CTAs of the launch build the coefficient stream `cs` themselves -- from rho (pro_mode 1, what
+    // pack_rho_kernel does) or straight from the statevectors (pro_mode 2: the partial trace rho = Psi Psi^dagger of
+    // every frame, optionally also written out as pro_rho_out) -- and meet at a grid-wide barrier (all CTAs of these
+    // persistent launches are co-resident).  pro_mode 0: `cs` was filled by an earlier launch.
+    int pro_mode;
+    double2 *cs_w;                    // writable alias of cs
+    const double2 *pro_rho;           // mode 1: [batch][N][ld]
+    int64_t pro_ld, pro_rho_stride;
+    const double2 *pro_psi;           // mode 2: pro_psi_batch statevectors, pro_psi_stride apart; frame f = set * pro_psi_batch + b
+    int64_t pro_psi_stride;           //         is the trace of statevector b with map `set` (layout of launch_trace_sv)
+    const TraceMap *pro_maps;
+    int pro_n_keep, pro_n_trace, pro_psi_batch;
+    double2 *pro_rho_out;             // mode 2, optional: [batch][N][N]
     // mirror-symmetric grids (wigner_sym_* kernels): U = ceil(S/2) mirror classes, U(U+1)/2 units per frame
     int sym, sym_U;
     int64_t sym_units;  // units this launch evaluates per frame ...
@@ -47,18 +69,15 @@ struct WigParams {
     int64_t sym_want_first, sym_want_count;  // caller's unit range (count < 0: all)
 };
 
-struct TraceMap {
-    // bit positions (ascending significance) of kept and traced qubits in the statevector index
-    int keep[kMaxQubits];
-    int trace[kMaxQubits];
-    int n_keep, n_trace;
-};
-
 cudaError_t launch_build_tab(double4 *tab, int N, cudaStream_t st);
 cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, int N, int batch, double2 *cs,
                             int64_t cs_stride, cudaStream_t st);
 cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches);
 bool patched_sass_available();
+// Load-time self-check of the re-scheduled SASS (once per device and process): every patched kernel variant and its
+// nvcc-scheduled twin evaluate the same probe grid; a variant whose results differ in any bit is reported in the
+// returned mask and runs nvcc's schedule from then on.  *checked receives the number of variants compared.
+cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *checked);
 // method="fft": scratch A [N][S] doubles, M [N][S], R [S][S], T [2S] complex; W is [S][S] (indexed [ip][ix])
 cudaError_t launch_wigner_fft(const double2 *rho, int N, int64_t ld, const double *d_xvec, int S, double g, double scale,
                               double *A, double2 *M, double2 *R, double2 *T, double *W, cudaStream_t st, int *launches);
@@ -69,6 +88,10 @@ size_t trace_sv_scratch_bytes(int n_keep, int n_trace, int batch, int n_sets);
 cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, const TraceMap *d_maps, int n_sets,
                             int n_keep, int n_trace, double2 *rho_out, double2 *partial, const DeviceInfo &dev,
                             cudaStream_t st, int *launches);
+// shot average: rho_out[set] = sum_b w_b rho[set][b] (d_weights NULL: 1 / batch); scratch as for launch_trace_sv
+cudaError_t launch_trace_sv_accumulate(const double2 *psi, int64_t psi_stride, int batch, const TraceMap *d_maps, int n_sets,
+                                       int n_keep, int n_trace, const double *d_weights, double2 *rho_out, double2 *partial,
+                                       const DeviceInfo &dev, cudaStream_t st, int *launches);
 // K2: density-matrix branch
 cudaError_t launch_trace_dm(const double2 *rho, int n_qubits, int batch, const TraceMap *d_map, int n_keep,
                             int n_trace, double2 *rho_out, cudaStream_t st, int *launches);

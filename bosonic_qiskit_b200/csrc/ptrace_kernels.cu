@@ -119,6 +119,31 @@ __global__ void reduce_splits_kernel(const double2 *__restrict__ partial, double
     out[i] = make_double2(re, im);
 }
 
+// Shot-averaged rho (util.py:523-532 collects one statevector per shot; tutorials/bosonic-kitten-code cell 14 averages
+// trace_out_qubits over them): out[set][i] = sum_b w_b sum_s partial[s][set][b][i], weights optional (NULL: 1 / batch),
+// fixed summation order.
+__global__ void reduce_shots_kernel(const double2 *__restrict__ partial, double2 *__restrict__ out, int64_t per_rho,
+                                    int n_sets, int batch, int splits, const double *__restrict__ weights)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_rho * n_sets) return;
+    const int64_t set = i / per_rho, e = i - set * per_rho;
+    const double uniform = 1.0 / (double)batch;
+    double re = 0.0, im = 0.0;
+    for (int b = 0; b < batch; ++b) {
+        double sr = 0.0, si = 0.0;
+        for (int s = 0; s < splits; ++s) {
+            const double2 v = partial[(((int64_t)s * n_sets + set) * batch + b) * per_rho + e];
+            sr += v.x;
+            si += v.y;
+        }
+        const double w = weights ? weights[b] : uniform;
+        re = fma(w, sr, re);
+        im = fma(w, si, im);
+    }
+    out[i] = make_double2(re, im);
+}
+
 namespace {
 struct TracePlan {
     int tiles, splits;
@@ -186,6 +211,40 @@ cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, c
         e = cudaGetLastError();
     }
     return e;
+}
+
+cudaError_t launch_trace_sv_accumulate(const double2 *psi, int64_t psi_stride, int batch, const TraceMap *d_maps, int n_sets,
+                                       int n_keep, int n_trace, const double *d_weights, double2 *rho_out, double2 *partial,
+                                       const DeviceInfo &dev, cudaStream_t st, int *launches)
+{
+    if (batch <= 0 || n_sets <= 0) return cudaSuccess;
+    const TracePlan pl = plan_trace(n_keep, n_trace, batch, n_sets, dev.sm_count);
+    TraceSvParams p;
+    p.psi = psi;
+    p.psi_stride = psi_stride;
+    p.maps = d_maps;
+    p.n_keep = n_keep;
+    p.n_trace = n_trace;
+    p.batch = batch;
+    p.n_sets = n_sets;
+    p.splits = pl.splits;
+    p.tiles = pl.tiles;
+    p.t_per_split = pl.t_per_split;
+    p.out = partial;  // always partials: the reduction also runs over the shots
+    const int64_t ydim = (int64_t)batch * n_sets;
+    const int64_t warps = (int64_t)pl.tiles * pl.tiles * pl.splits;
+    const int64_t xdim = (warps + kTraceWarps - 1) / kTraceWarps;
+    if (ydim > 65535 || xdim > 0x7fffffffLL) return cudaErrorInvalidValue;
+    trace_sv_dmma_kernel<<<dim3((unsigned)xdim, (unsigned)ydim), 32 * kTraceWarps, 0, st>>>(p);
+    if (launches) ++*launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int64_t D = (int64_t)1 << n_keep;
+    const int64_t count = (int64_t)n_sets * D * D;
+    reduce_shots_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partial, rho_out, D * D, n_sets, batch, pl.splits,
+                                                                       d_weights);
+    if (launches) ++*launches;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

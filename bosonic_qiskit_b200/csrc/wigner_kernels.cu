@@ -16,6 +16,9 @@
 //     (1-D TMA) + mbarrier full/empty pairs, one elected producer thread, every warp a consumer;
 //   * persistent CTAs take tiles from a global counter so that all 148 SMs finish together;
 //   * stores are 32 B per thread, 1 KiB contiguous per warp, streaming (evict-first).
+#include <cstring>
+#include <vector>
+
 #include "bq_common.cuh"
 #include "bq_internal.h"
 
@@ -106,9 +109,157 @@ __device__ __forceinline__ void leave_grid(const WigParams &p)
         if (done == gridDim.x - 1) {
             p.ctr[0] = 0u;
             p.ctr[1] = 0u;
+            p.ctr[2] = 0u;
             __threadfence();
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused prologue: the launch builds its own coefficient stream (WigParams::pro_mode), then all CTAs meet at a
+// grid-wide barrier.  One launch per step instead of four (trace partial sums, split reduction, pack, Wigner):
+// at cutoff 64 / 1024^2 those three small launches and the gaps between them were 21 us of a 165 us step, at
+// cutoff 16 / 200^2 more than half of it.  Kept out of line so the hot kernels' register allocation does not see it.
+//   mode 1: cs <- rho                (what pack_rho_kernel does; one warp per diagonal)
+//   mode 2: cs <- Psi Psi^dagger     (the partial trace of util.py:580,596,619,693; one warp -- or, for fewer than 32
+//                                     traced indices, one thread -- per element (i, j >= i) of every frame's rho,
+//                                     fixed summation order; optionally the full rho goes to pro_rho_out)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pro_deposit(uint64_t v, const int *__restrict__ pos, int n)
+{
+    uint64_t r = 0;
+    for (int b = 0; b < n; ++b) r |= ((v >> b) & 1ull) << __ldg(pos + b);
+    return r;
+}
+
+// element (i, j), i <= j, of frame `frame` -> its record(s) of the coefficient stream (+ rho_out)
+__device__ __forceinline__ void pro_emit(const WigParams &p, int64_t frame, int i, int j, double re, double im)
+{
+    const int N = p.N;
+    double2 *C = p.cs_w + frame * p.cs_stride;
+    const int L = j - i;
+    if (L == N - 1) {
+        C[0] = make_double2(2.0 * re, 2.0 * im);  // header: 2 rho[0, N-1]
+    } else {
+        const int K = N - L;
+        const double f = (L == 0) ? 1.0 : 2.0;
+        const int64_t pos = diag_pos(K);
+        C[pos + (K - 1 - i)] = make_double2(f * re, f * im);
+        if (i == 0) C[pos + K] = make_double2(0.0, 0.0);  // the diagonal's tail record carries no coefficient
+    }
+    if (p.pro_rho_out) {
+        double2 *R = p.pro_rho_out + frame * (int64_t)N * N;
+        R[(int64_t)i * N + j] = make_double2(re, im);
+        if (i != j) R[(int64_t)j * N + i] = make_double2(re, -im);
+    }
+}
+
+// row-by-row index over the upper triangle (row i holds j = i .. N-1) -> (i, j)
+__device__ __forceinline__ void pro_tri(int64_t q, int N, int &i, int &j)
+{
+    const double w = 2.0 * N + 1.0;
+    int r = (int)((w - sqrt(w * w - 8.0 * (double)q)) * 0.5);
+    r = max(0, min(r, N - 1));
+    while (r > 0 && (int64_t)r * N - (int64_t)r * (r - 1) / 2 > q) --r;
+    while (r + 1 < N && (int64_t)(r + 1) * N - (int64_t)(r + 1) * r / 2 <= q) ++r;
+    i = r;
+    j = r + (int)(q - ((int64_t)r * N - (int64_t)r * (r - 1) / 2));
+}
+
+__device__ __noinline__ void fused_prologue(const WigParams &p)
+{
+    const int lane = threadIdx.x & 31;
+    const int wpc = blockDim.x >> 5;
+    const int64_t gwarp = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * wpc;
+    const int N = p.N;
+    if (p.pro_mode == 1) {
+        // one warp per (frame, diagonal K = 1 .. N): K = 1 is the header, K >= 2 the K step records + the tail record
+        const int64_t items = (int64_t)p.batch * N;
+        for (int64_t it = gwarp; it < items; it += nwarps) {
+            const int64_t frame = it / N;
+            const int K = (int)(it - frame * N) + 1;
+            const double2 *R = p.pro_rho + frame * p.pro_rho_stride;
+            double2 *C = p.cs_w + frame * p.cs_stride;
+            if (K == 1) {
+                if (lane == 0) {
+                    const double2 v = R[N - 1];
+                    C[0] = make_double2(2.0 * v.x, 2.0 * v.y);
+                }
+                continue;
+            }
+            const int L = N - K;
+            const double f = (L == 0) ? 1.0 : 2.0;
+            const int64_t pos = diag_pos(K);
+            for (int r = lane; r <= K; r += 32) {
+                double2 v = make_double2(0.0, 0.0);
+                if (r < K) {
+                    const int j = K - 1 - r;
+                    const double2 e = R[(int64_t)j * p.pro_ld + j + L];
+                    v = make_double2(f * e.x, f * e.y);
+                }
+                C[pos + r] = v;
+            }
+        }
+    } else if (p.pro_mode == 2) {
+        const int nk = p.pro_n_keep, nt = p.pro_n_trace;
+        const int64_t T = (int64_t)1 << nt;
+        const int64_t ntri = (int64_t)N * (N + 1) / 2, items = (int64_t)p.batch * ntri;
+        const bool per_thread = T < 32;  // few traced indices: one thread per element, no shuffles
+        const int64_t first = per_thread ? gwarp * 32 + lane : gwarp, stride = per_thread ? nwarps * 32 : nwarps;
+        for (int64_t it = first; it < items; it += stride) {
+            const int64_t frame = it / ntri;
+            int i, j;
+            pro_tri(it - frame * ntri, N, i, j);
+            const int set = (int)(frame / p.pro_psi_batch);
+            const int64_t b = frame - (int64_t)set * p.pro_psi_batch;
+            const TraceMap *map = p.pro_maps + set;
+            const double2 *psi = p.pro_psi + b * p.pro_psi_stride;
+            const uint64_t row_i = pro_deposit((uint64_t)i, map->keep, nk), row_j = pro_deposit((uint64_t)j, map->keep, nk);
+            uint64_t mask = 0;
+            for (int q = 0; q < nt; ++q) mask |= 1ull << __ldg(map->trace + q);
+            double re = 0.0, im = 0.0;
+            if (per_thread) {
+                const uint64_t step = pro_deposit(1ull, map->trace, nt);
+                uint64_t toff = 0;
+                for (int64_t t = 0; t < T; ++t) {
+                    const double2 x = psi[row_i | toff], y = psi[row_j | toff];
+                    re = fma(x.x, y.x, fma(x.y, y.y, re));   // x conj(y)
+                    im = fma(x.y, y.x, fma(-x.x, y.y, im));
+                    toff = ((toff | ~mask) + step) & mask;
+                }
+                pro_emit(p, frame, i, j, re, im);
+            } else {
+                const uint64_t step = pro_deposit(32ull, map->trace, nt);
+                uint64_t toff = pro_deposit((uint64_t)lane, map->trace, nt);
+                for (int64_t t = lane; t < T; t += 32) {
+                    const double2 x = psi[row_i | toff], y = psi[row_j | toff];
+                    re = fma(x.x, y.x, fma(x.y, y.y, re));
+                    im = fma(x.y, y.x, fma(-x.x, y.y, im));
+                    toff = ((toff | ~mask) + step) & mask;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    re += __shfl_down_sync(0xffffffffu, re, off);
+                    im += __shfl_down_sync(0xffffffffu, im, off);
+                }
+                if (lane == 0) pro_emit(p, frame, i, j, re, im);
+            }
+        }
+    }
+    // grid-wide barrier: every CTA of the launch is resident (grid <= occupancy x SMs, see run())
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&p.ctr[2], 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ctr + 2) : "memory");
+            if (seen < gridDim.x) __nanosleep(64);
+        } while (seen < gridDim.x);
+        // the stream is read next by bulk copies (async proxy): order them after the generic-proxy writes seen above
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,6 +407,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_resident_kernel(const Wi
     uint32_t phase = 0;
     int loaded_frame = -1;
     TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
     const int N = p.N;
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
@@ -362,6 +514,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_diag_kernel(const WigParams
 
     uint32_t full_phase = 0, fill_count = 0;  // per-stage phase parities (see wigner_stream_kernel)
     TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
         const int frame = tile / p.tiles_per_frame;
@@ -512,13 +665,6 @@ __device__ __forceinline__ void sym_tail(SymPoints<CL> &s, const double4 t)
     }
 }
 
-// Rotated trip (loads of step r + 4 issued right after step r): measured SLOWER (profiles/r1d_sym_variants_rotated.txt:
-// cutoff 64 / 2048^2 0.575 vs 0.495 ms, cutoff 1024 / 4096^2 459 vs 421 ms) because the SASS re-scheduler leaves a loop
-// with loop-carried loads alone, and its operand-reuse chains are worth more than the hidden LDS latency.  Off.
-#ifndef BQ_SYM_ROTATE
-#define BQ_SYM_ROTATE 0
-#endif
-
 // the steps of one diagonal (everything but its tail); returns the tail record
 template <int CL, typename P>
 __device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__restrict__ cd,
@@ -540,35 +686,6 @@ __device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__res
     int r = 0;
     // four steps per trip: with 5 CL DFMAs per step the loop control and the load latency of a two-step body
     // showed as `wait` stalls (fp64 pipe 72 % busy at N = 256)
-#if BQ_SYM_ROTATE
-    // ... and the trip is ROTATED: the coefficients of step r + 4 are loaded right after step r has consumed its own,
-    // into the same registers, so no trip starts by waiting for shared memory (the loads at the loop top were 20 % of
-    // the stall samples of the cutoff-1024 kernel: two warps per scheduler cannot hide a 29-cycle LDS)
-    if (m >= 4) {
-        double2 c0 = cp[0], c1 = cp[1], c2 = cp[2], c3 = cp[3];
-        double4 t0 = tp[0], t1 = tp[1], t2 = tp[2], t3 = tp[3];
-#pragma unroll 1
-        for (; r + 7 < m; r += 4) {
-            sym_step<CL>(s, c0, t0);
-            c0 = cp[r + 4];
-            t0 = tp[r + 4];
-            sym_step<CL>(s, c1, t1);
-            c1 = cp[r + 5];
-            t1 = tp[r + 5];
-            sym_step<CL>(s, c2, t2);
-            c2 = cp[r + 6];
-            t2 = tp[r + 6];
-            sym_step<CL>(s, c3, t3);
-            c3 = cp[r + 7];
-            t3 = tp[r + 7];
-        }
-        sym_step<CL>(s, c0, t0);
-        sym_step<CL>(s, c1, t1);
-        sym_step<CL>(s, c2, t2);
-        sym_step<CL>(s, c3, t3);
-        r += 4;
-    }
-#else
 #pragma unroll 1
     for (; r + 3 < m; r += 4) {
         sym_step<CL>(s, cp[r], tp[r]);
@@ -576,7 +693,6 @@ __device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__res
         sym_step<CL>(s, cp[r + 2], tp[r + 2]);
         sym_step<CL>(s, cp[r + 3], tp[r + 3]);
     }
-#endif
 #pragma unroll 1
     for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
     return tp[m];
@@ -588,72 +704,6 @@ __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__
 {
     const double4 t = sym_diagonal_steps<CL>(s, cd, td, K);
     sym_tail<CL>(s, t);
-}
-
-// Steps of one diagonal with DOUBLE-BUFFERED coefficients (kernels that have the registers for a second set of
-// four steps' coefficients): while the four steps of one set run, the other set is being loaded, so no DFMA waits
-// for shared memory.  Same steps in the same order as sym_diagonal_steps.  NOT USED: measured on the parked kernel
-// (round 1), ptxas software-pipelines the 8-step trip and the cutoff-1024 grid took 382 ms against 380 ms -- the
-// exposed shared-memory latency the stall samples show is not what bounds the kernel -- and the re-scheduled image of
-// that loop produced NaNs (registers time-shared between addresses and FP64 values across the back edge).
-template <int CL, typename P>
-__device__ __forceinline__ double4 sym_diagonal_steps_db(P &s, const double2 *__restrict__ cd,
-                                                         const double4 *__restrict__ td, const int K)
-{
-    {
-        const double2 c1 = cd[0], c0 = cd[1];
-#pragma unroll
-        for (int k = 0; k < CL; ++k) {
-            s.y1r[k] = c1.x;
-            s.y1i[k] = c1.y;
-            s.y0r[k] = c0.x;
-            s.y0i[k] = c0.y;
-        }
-    }
-    const double2 *cp = cd + 2;
-    const double4 *tp = td + 2;
-    const int m = K - 2;
-    int r = 0;
-    if (m >= 12) {
-        double2 ca0 = cp[0], ca1 = cp[1], ca2 = cp[2], ca3 = cp[3];
-        double4 ta0 = tp[0], ta1 = tp[1], ta2 = tp[2], ta3 = tp[3];
-#pragma unroll 1
-        for (; r + 11 < m; r += 8) {
-            const double2 cb0 = cp[r + 4], cb1 = cp[r + 5], cb2 = cp[r + 6], cb3 = cp[r + 7];
-            const double4 tb0 = tp[r + 4], tb1 = tp[r + 5], tb2 = tp[r + 6], tb3 = tp[r + 7];
-            sym_step<CL>(s, ca0, ta0);
-            sym_step<CL>(s, ca1, ta1);
-            sym_step<CL>(s, ca2, ta2);
-            sym_step<CL>(s, ca3, ta3);
-            ca0 = cp[r + 8];
-            ca1 = cp[r + 9];
-            ca2 = cp[r + 10];
-            ca3 = cp[r + 11];
-            ta0 = tp[r + 8];
-            ta1 = tp[r + 9];
-            ta2 = tp[r + 10];
-            ta3 = tp[r + 11];
-            sym_step<CL>(s, cb0, tb0);
-            sym_step<CL>(s, cb1, tb1);
-            sym_step<CL>(s, cb2, tb2);
-            sym_step<CL>(s, cb3, tb3);
-        }
-        sym_step<CL>(s, ca0, ta0);
-        sym_step<CL>(s, ca1, ta1);
-        sym_step<CL>(s, ca2, ta2);
-        sym_step<CL>(s, ca3, ta3);
-        r += 4;
-    }
-#pragma unroll 1
-    for (; r + 3 < m; r += 4) {
-        sym_step<CL>(s, cp[r], tp[r]);
-        sym_step<CL>(s, cp[r + 1], tp[r + 1]);
-        sym_step<CL>(s, cp[r + 2], tp[r + 2]);
-        sym_step<CL>(s, cp[r + 3], tp[r + 3]);
-    }
-#pragma unroll 1
-    for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
-    return tp[m];
 }
 
 // Tail with the eight Horner accumulators of every unit in shared memory, acc[(unit slot * 8 + k) * THREADS + tid]
@@ -750,6 +800,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_sym_resident_kernel(cons
     uint32_t phase = 0;
     int loaded_frame = -1;
     TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
     const int N = p.N;
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
@@ -806,6 +857,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
 
     uint32_t full_phase = 0, fill_count = 0;
     TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
         const int frame = tile / p.tiles_per_frame;
@@ -894,6 +946,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184
 
     uint32_t full_phase = 0, fill_count = 0;
     TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
         const int frame = tile / p.tiles_per_frame;
@@ -1005,6 +1058,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_stream_kernel(const WigPara
     uint32_t full_phase = 0;   // bit st: parity the consumers wait for next on full[st]
     uint32_t fill_count = 0;   // bit st: parity of the number of times stage st has been filled (producer thread)
     TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
         const int frame = tile / p.tiles_per_frame;
@@ -1172,7 +1226,7 @@ const Patched &patched_kernels()
 cudaError_t occupancy(const void *plain, int variant, int threads, size_t smem, DeviceInfo &dev, const void **func_out,
                       int *occ_out)
 {
-    const bool use_patched = dev.sass_mode != 0 && patched_kernels().ok;
+    const bool use_patched = dev.sass_mode != 0 && patched_kernels().ok && !((dev.patched_bad >> variant) & 1ull);
     const void *func = use_patched ? patched_kernels().func[variant] : plain;
     const int slot = variant + (use_patched ? kVariants : 0);
     cudaError_t e;
@@ -1222,6 +1276,199 @@ cudaError_t run(const void *plain, int variant, int threads, size_t smem, WigPar
 }  // namespace
 
 bool patched_sass_available() { return patched_kernels().ok; }
+
+// ------------------------------------------------------------------------------------------------
+// Load-time self-check of the re-scheduled SASS.  The patched image re-orders DFMAs and rewrites control bits of an
+// undocumented encoding; its arithmetic is meant to be unchanged, so a patched variant must reproduce its
+// nvcc-scheduled twin BIT FOR BIT.  Every variant is run both ways on a small probe (cutoff 24 for the resident
+// kernels, 80 for the ring / streaming ones; a mirror-symmetric 40 x 40 grid, two frames); any difference, fault or
+// launch error disqualifies the patched image of that variant for this process.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct VariantInfo {
+    const void *plain;
+    int kind;  // 0 resident, 1 stream, 2 diag ring, 3 sym resident, 4 sym ring, 5 sym ring with parked accumulators
+    int pts, threads, stages;
+};
+const VariantInfo kVariantInfo[kVariants] = {
+    {(const void *)wigner_resident_kernel<4, 256, 2>, 0, 4, 256, 0},
+    {(const void *)wigner_resident_kernel<2, 128, 4>, 0, 2, 128, 0},
+    {(const void *)wigner_resident_kernel<1, 128, 4>, 0, 1, 128, 0},
+    {(const void *)wigner_stream_kernel<4, 256, kStages, kChunk>, 1, 4, 256, kStages},
+    {(const void *)wigner_stream_kernel<2, 128, kStages, kChunk>, 1, 2, 128, kStages},
+    {(const void *)wigner_resident_kernel<8, 128, 2>, 0, 8, 128, 0},
+    {(const void *)wigner_stream_kernel<8, 128, kStages, kChunk>, 1, 8, 128, kStages},
+    {(const void *)wigner_diag_kernel<8, 256, kDiagStages>, 2, 8, 256, kDiagStages},
+    {(const void *)wigner_sym_resident_kernel<3, 128, 2>, 3, 3, 128, 0},
+    {(const void *)wigner_sym_resident_kernel<1, 128, 4>, 3, 1, 128, 0},
+    {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 4, 3, 256, kDiagStages},
+    {(const void *)wigner_sym_resident_kernel<2, 128, 2>, 3, 2, 128, 0},
+    {(const void *)wigner_sym_resident_kernel<2, 192, 2>, 3, 2, 192, 0},
+    {(const void *)wigner_sym_resident_kernel<1, 256, 2>, 3, 1, 256, 0},
+    {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 4, 2, 256, kDiagStages},
+    {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 4, 2, 384, kDiagStages},
+    {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 4, 1, 256, kDiagStages},
+    {(const void *)wigner_sym_resident_kernel<4, 256, 1>, 3, 4, 256, 0},
+    {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 4, 4, 256, kDiagStages},
+    {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2>, 5, 4, 256, 2},
+    {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2>, 5, 3, 384, 2},
+};
+
+size_t variant_smem(const VariantInfo &v, int N, int R_tot)
+{
+    switch (v.kind) {
+    case 0: return (size_t)R_tot * 48 + 64 + 1024 * sizeof(double);
+    case 1: return (size_t)v.stages * kChunk * 48 + 2 * v.stages * 8 + 64;
+    case 2: return (((size_t)v.stages * (N + 1) * 48 + 2 * v.stages * 8 + 64 + 15) & ~(size_t)15) + 2048 * sizeof(double);
+    case 3: return (size_t)R_tot * 48 + 64;
+    case 4: return (size_t)v.stages * (N + 1) * 48 + 2 * v.stages * 8 + 64;
+    default: {
+        const size_t ring = (size_t)v.stages * (N + 1) * 48 + 2 * v.stages * 8 + 64;
+        return ((ring + 15) & ~(size_t)15) + (size_t)v.pts * 8 * v.threads * sizeof(double2);
+    }
+    }
+}
+}  // namespace
+
+cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *checked)
+{
+    *bad_mask = 0;
+    *checked = 0;
+    if (!patched_kernels().ok) return cudaSuccess;
+    constexpr int S = 40, FRAMES = 2;
+    const int cutoffs[2] = {24, 80};
+    const int saved_mode = dev.sass_mode;
+    const uint64_t saved_bad = dev.patched_bad;
+    dev.patched_bad = 0;
+    cudaStream_t st = nullptr;
+    cudaError_t err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (err != cudaSuccess) return err;
+    double *d_x = nullptr, *d_W = nullptr;
+    double2 *d_rho = nullptr, *d_cs = nullptr;
+    double4 *d_tab = nullptr;
+    unsigned int *d_ctr = nullptr;
+    std::vector<double> x(S), Wa((size_t)FRAMES * S * S), Wb(Wa.size());
+    for (int i = 0; i < S / 2; ++i) {
+        x[i] = -3.0 + 6.0 * i / (S - 1);
+        x[S - 1 - i] = -x[i];
+    }
+    auto cleanup = [&]() {
+        cudaFree(d_x);
+        cudaFree(d_W);
+        cudaFree(d_rho);
+        cudaFree(d_cs);
+        cudaFree(d_tab);
+        cudaFree(d_ctr);
+        cudaStreamDestroy(st);
+        dev.sass_mode = saved_mode;
+    };
+#define VCHK(call)                      \
+    do {                                \
+        err = (call);                   \
+        if (err != cudaSuccess) {       \
+            cleanup();                  \
+            dev.patched_bad = saved_bad; \
+            return err;                 \
+        }                               \
+    } while (0)
+    VCHK(cudaMalloc(&d_x, sizeof(double) * S));
+    VCHK(cudaMalloc(&d_W, sizeof(double) * Wa.size()));
+    VCHK(cudaMalloc(&d_ctr, sizeof(unsigned int) * 4));
+    VCHK(cudaMemcpyAsync(d_x, x.data(), sizeof(double) * S, cudaMemcpyHostToDevice, st));
+    uint64_t bad = 0;
+    int n_checked = 0;
+    for (int ci = 0; ci < 2; ++ci) {
+        const int N = cutoffs[ci];
+        const int R = (int)stream_records(N);
+        // probe rho: a fixed pseudo-random Hermitian matrix with decaying entries (no symmetry the kernels could hide behind)
+        std::vector<double2> rho((size_t)FRAMES * N * N);
+        uint64_t lcg = 0x9E3779B97F4A7C15ull + (uint64_t)N;
+        auto rnd = [&]() {
+            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+            return (double)((lcg >> 11) & ((1ull << 53) - 1)) / (double)(1ull << 53) - 0.5;
+        };
+        for (int f = 0; f < FRAMES; ++f)
+            for (int i = 0; i < N; ++i)
+                for (int j = i; j < N; ++j) {
+                    const double damp = 1.0 / (1.0 + 0.2 * (i + j));
+                    const double re = rnd() * damp, im = (i == j) ? 0.0 : rnd() * damp;
+                    rho[((size_t)f * N + i) * N + j] = make_double2(re, im);
+                    rho[((size_t)f * N + j) * N + i] = make_double2(re, -im);
+                }
+        cudaFree(d_rho);
+        cudaFree(d_cs);
+        cudaFree(d_tab);
+        d_rho = nullptr;
+        d_cs = nullptr;
+        d_tab = nullptr;
+        VCHK(cudaMalloc(&d_rho, sizeof(double2) * rho.size()));
+        VCHK(cudaMalloc(&d_cs, sizeof(double2) * (size_t)FRAMES * R));
+        VCHK(cudaMalloc(&d_tab, sizeof(double4) * (size_t)R));
+        VCHK(cudaMemcpyAsync(d_rho, rho.data(), sizeof(double2) * rho.size(), cudaMemcpyHostToDevice, st));
+        VCHK(launch_build_tab(d_tab, N, st));
+        for (int v = 0; v < kVariants; ++v) {
+            const VariantInfo &vi = kVariantInfo[v];
+            const bool resident_kind = vi.kind == 0 || vi.kind == 3;
+            if (resident_kind != (N <= kResidentMaxN)) continue;
+            const size_t smem = variant_smem(vi, N, R);
+            if (smem > dev.smem_optin) continue;
+            bool ok = true;
+            for (int pass = 0; pass < 2 && ok; ++pass) {
+                WigParams p{};
+                p.cs = d_cs;
+                p.cs_w = d_cs;
+                p.pro_mode = 1;
+                p.pro_rho = d_rho;
+                p.pro_ld = N;
+                p.pro_rho_stride = (int64_t)N * N;
+                p.tab = d_tab;
+                p.xvec = d_x;
+                p.yvec = d_x;
+                p.W = d_W;
+                p.w_stride = (int64_t)S * S;
+                p.cs_stride = R;
+                p.N = N;
+                p.R_tot = R;
+                p.nx = S;
+                p.ny = S;
+                p.batch = FRAMES;
+                p.g = 1.4142135623730951;
+                p.scale = 1.0 / 3.14159265358979323846;
+                p.ctr = d_ctr;
+                p.sym = vi.kind >= 3;
+                p.sym_U = (S + 1) / 2;
+                p.sym_units = (int64_t)p.sym_U * (p.sym_U + 1) / 2;
+                p.sym_first = 0;
+                p.sym_want_count = -1;
+                dev.sass_mode = pass;  // 0: nvcc's schedule, 1: the patched image
+                VCHK(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned int) * 4, st));
+                VCHK(cudaMemsetAsync(d_W, 0xFF, sizeof(double) * Wa.size(), st));
+                const int64_t sym_chunks = p.sym ? (p.sym_units + vi.pts - 1) / vi.pts : -1;
+                cudaError_t e = run(vi.plain, v, vi.threads, smem, p, vi.pts, dev, st, nullptr, sym_chunks);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(pass ? Wb.data() : Wa.data(), d_W, sizeof(double) * Wa.size(), cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    if (pass == 0) {  // the plain kernel itself cannot run this probe: nothing to compare
+                        ok = false;
+                        break;
+                    }
+                    bad |= 1ull << v;
+                    ok = false;
+                }
+            }
+            if (!ok) continue;
+            ++n_checked;
+            if (std::memcmp(Wa.data(), Wb.data(), sizeof(double) * Wa.size()) != 0) bad |= 1ull << v;
+        }
+    }
+#undef VCHK
+    cleanup();
+    dev.patched_bad = saved_bad | bad;
+    *bad_mask = bad;
+    *checked = n_checked;
+    return cudaSuccess;
+}
 
 // Chooses the tile shape so that small grids still cover every SM, then launches.
 cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *launches)
@@ -1310,10 +1557,13 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 c.round_cost = (double)v.cl * v.threads * occ / eff;
             }
         }
+        bool pro_done = false;  // the fused prologue builds the coefficient stream once: in the first launch of the call
         auto launch_range = [&](const SymVariant &v, int64_t first, int64_t count) {
             WigParams q = p;
             q.sym_first = first;
             q.sym_units = count;
+            if (pro_done) q.pro_mode = 0;
+            pro_done = true;
             return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, (count + v.cl - 1) / v.cl);
         };
         // A last round that fills only part of the machine still costs a whole tile.  Tried and measured (tools/

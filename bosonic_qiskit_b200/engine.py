@@ -105,6 +105,12 @@ class Engine:
         check(self._lib.bq_set_sass_mode(self._h, 1 if patched else 0, ctypes.byref(active)))
         return bool(active.value)
 
+    def sass_self_check(self) -> tuple[int, int]:
+        """(mask of kernel variants whose re-scheduled SASS failed the load-time bit-identity check, variants checked)."""
+        bad, n = ctypes.c_uint64(), ctypes.c_int()
+        check(self._lib.bq_sass_self_check(self._h, ctypes.byref(bad), ctypes.byref(n)))
+        return int(bad.value), int(n.value)
+
     def set_grid_sharing(self, on: bool) -> None:
         """Mirror-symmetric grids (``yvec == xvec == -xvec[::-1]``, what the reference always builds): share the
         inner Clenshaw recurrence between the eight points of equal ``x**2 + p**2`` (default on).  Off = always the
@@ -252,6 +258,77 @@ class Engine:
         check(self._lib.bq_partial_trace_sv_multi_host(self._h, _ptr(psi), n, _int_array(flat), nt, len(sets),
                                                        _ptr(out)))
         return out
+
+    def partial_trace_sv_mean(self, psi, traced: Sequence[int], weights=None) -> np.ndarray:
+        """Shot-averaged reduced density matrix: ``psi`` (shots, dim) -> ``sum_k w_k Tr_traced |psi_k><psi_k|`` (D, D),
+        ``weights=None`` being the plain mean.  One batched launch (``bq_partial_trace_sv_accumulate_host``)."""
+        psi = _c128(psi)
+        if psi.ndim != 2 or psi.shape[0] == 0:
+            raise ValueError("psi must be (shots, dim) with at least one shot")
+        shots, dim = psi.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        D = 1 << (n - len(traced)) if len(traced) <= n else 0
+        w = None
+        if weights is not None:
+            w = _f64(weights).reshape(-1)
+            if w.shape[0] != shots:
+                raise ValueError("weights must have one entry per shot")
+        out = np.empty((D, D), dtype=np.complex128)
+        check(self._lib.bq_partial_trace_sv_accumulate_host(self._h, _ptr(psi), n, _int_array(traced), len(traced), shots,
+                                                            dim, _ptr(w) if w is not None else None, _ptr(out)))
+        return out
+
+    def partial_trace_sv_mean_t(self, psi, traced: Sequence[int], weights=None, out=None, stream=None):
+        """Device-resident ``partial_trace_sv_mean``: ``psi`` (shots, dim) complex128 CUDA tensor -> (D, D) tensor."""
+        import torch
+
+        self._check_tensor(psi, torch.complex128, "psi")
+        if psi.dim() != 2 or psi.shape[0] == 0:
+            raise ValueError("psi must be (shots, dim) with at least one shot")
+        shots, dim = psi.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        D = 1 << max(n - len(traced), 0)
+        if weights is not None:
+            self._check_tensor(weights, torch.float64, "weights")
+        if out is None:
+            out = torch.empty((D, D), dtype=torch.complex128, device=psi.device)
+        check(self._lib.bq_partial_trace_sv_accumulate_dev(
+            self._h, ctypes.c_void_p(psi.data_ptr()), n, _int_array(traced), len(traced), shots, dim,
+            ctypes.c_void_p(weights.data_ptr()) if weights is not None else None, ctypes.c_void_p(out.data_ptr()),
+            self._stream_ptr(stream)))
+        return out
+
+    def state_to_wigner_multi(self, psi, traced_sets: Sequence[Sequence[int]], xvec, yvec=None, g: float = math.sqrt(2),
+                              method: str = "clenshaw", return_rho: bool = False, out=None):
+        """Several traces of ONE statevector, each followed by its Wigner grid, in one call (per-site reduced density
+        matrices + per-site Wigner functions): ``psi`` (dim,) -> W (n_sets, ny, nx) [, rho (n_sets, D, D)]."""
+        code = method_code(method)
+        psi = _c128(psi).reshape(-1)
+        n = _n_qubits(psi.shape[0])
+        sets = [list(s) for s in traced_sets]
+        nt = len(sets[0]) if sets else 0
+        if any(len(s) != nt for s in sets):
+            raise ValueError("all traced sets must have the same length")
+        if code == METHODS["fft"]:
+            rho_f = self.partial_trace_sv_multi(psi, sets)
+            res = self.wigner_fft(rho_f, xvec, g=g)
+            return (res, rho_f) if return_rho else res
+        xvec = _f64(xvec).reshape(-1)
+        yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
+        shape = (len(sets), len(yvec), len(xvec))
+        if out is None:
+            out = self.pinned_empty(shape, np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape / dtype / layout")
+        D = 1 << max(n - nt, 0)
+        rho = np.empty((len(sets), D, D), dtype=np.complex128) if return_rho else None
+        flat = [q for s in sets for q in s]
+        check(self._lib.bq_state_to_wigner_multi_host(
+            self._h, _ptr(psi), n, _int_array(flat), nt, len(sets), _ptr(xvec), len(xvec), _ptr(yvec), len(yvec), float(g),
+            code, _ptr(out), _ptr(rho) if return_rho else None))
+        return (out, rho) if return_rho else out
 
     def partial_trace_dm(self, rho, traced: Sequence[int]) -> np.ndarray:
         rho = _c128(rho)
@@ -476,6 +553,10 @@ class Engine:
                 if self._stage is None or self._stage.numel() < n_out or self._stage.device != psi.device:
                     self._stage = torch.empty((n_out,), dtype=torch.float64, device=psi.device)
                 stage = self._stage
+                if stream is not None:
+                    # the block is read by a copy on `stream`: tell torch's caching allocator, so that a later
+                    # re-allocation of the staging block cannot hand its memory out while that copy is in flight
+                    stage.record_stream(stream)
                 out_ptr = stage.data_ptr()
             check(self._lib.bq_set_grid_symmetry(self._h, mode))
             check(self._lib.bq_state_to_wigner_dev(
@@ -489,6 +570,33 @@ class Engine:
         if isinstance(out, int):
             return None
         return out[0] if single else out
+
+    def state_to_wigner_multi_t(self, psi, traced_sets: Sequence[Sequence[int]], xvec, yvec=None, g: float = math.sqrt(2),
+                                method: str = "clenshaw", out=None, rho_out=None, stream=None):
+        """Device-resident ``state_to_wigner_multi``: one statevector tensor -> (n_sets, ny, nx) tensor."""
+        import torch
+
+        code = method_code(method)
+        self._check_tensor(psi, torch.complex128, "psi")
+        psi = psi.reshape(-1)
+        n = _n_qubits(psi.numel())
+        sets = [list(s) for s in traced_sets]
+        nt = len(sets[0]) if sets else 0
+        if any(len(s) != nt for s in sets):
+            raise ValueError("all traced sets must have the same length")
+        yvec = xvec if yvec is None else yvec
+        self._check_tensor(xvec, torch.float64, "xvec")
+        self._check_tensor(yvec, torch.float64, "yvec")
+        if out is None:
+            out = torch.empty((len(sets), yvec.numel(), xvec.numel()), dtype=torch.float64, device=psi.device)
+        flat = [q for s in sets for q in s]
+        with self._grid_lock:
+            check(self._lib.bq_set_grid_symmetry(self._h, self._device_grid_mode(xvec, yvec)))
+            check(self._lib.bq_state_to_wigner_multi_dev(
+                self._h, ctypes.c_void_p(psi.data_ptr()), n, _int_array(flat), nt, len(sets), ctypes.c_void_p(xvec.data_ptr()),
+                xvec.numel(), ctypes.c_void_p(yvec.data_ptr()), yvec.numel(), float(g), code, ctypes.c_void_p(out.data_ptr()),
+                ctypes.c_void_p(rho_out.data_ptr()) if rho_out is not None else None, self._stream_ptr(stream)))
+        return out
 
     def frame_minmax_t(self, W, stream=None):
         import torch
@@ -544,6 +652,147 @@ class Engine:
         check(self._lib.bq_ipc_close(self._h, ctypes.c_void_p(ptr)))
 
 
+class MultiEngine:
+    """All (or some of) the GPUs of one box from ONE process: owns a ``bq_multi_t`` (one handle + one worker thread per
+    device).  Replaces the reference's ``multiprocessing.Pool`` over frames (``animate.py:166-169,191-206``).
+
+    ``shard="frames"``: contiguous frame blocks per GPU, each GPU writes its finished grids into its slice of the
+    (page-locked) result; ``shard="grid"``: ONE large grid shared out over the GPUs (``BQ_SHARD_GRID``)."""
+
+    def __init__(self, devices: Sequence[int] | None = None):
+        self._lib = _lib.load()
+        m = ctypes.c_void_p()
+        if devices is None:
+            check(self._lib.bq_multi_init(ctypes.byref(m), 0, None))
+        else:
+            devs = [int(d) for d in devices]
+            check(self._lib.bq_multi_init(ctypes.byref(m), len(devs), _int_array(devs)))
+        self._m = m
+        self._finalizer = weakref.finalize(self, self._lib.bq_multi_finalize, m)
+        n = ctypes.c_int()
+        check(self._lib.bq_multi_device_count(self._m, ctypes.byref(n)))
+        self.n_devices = int(n.value)
+        h0 = ctypes.c_void_p()
+        check(self._lib.bq_multi_handle(self._m, 0, ctypes.byref(h0)))
+        self._h0 = h0  # page-locked buffers are portable: allocated through the first device's handle
+        self._pinned: dict[tuple, np.ndarray] = {}
+
+    def close(self) -> None:
+        self._pinned.clear()
+        self._finalizer()
+
+    @property
+    def launches(self) -> int:
+        n = ctypes.c_uint64()
+        check(self._lib.bq_multi_launch_count(self._m, ctypes.byref(n)))
+        return int(n.value)
+
+    def handle(self, index: int):
+        h = ctypes.c_void_p()
+        check(self._lib.bq_multi_handle(self._m, int(index), ctypes.byref(h)))
+        return h
+
+    def set_sass_mode(self, patched: bool) -> None:
+        for k in range(self.n_devices):
+            check(self._lib.bq_set_sass_mode(self.handle(k), 1 if patched else 0, None))
+
+    def pinned_empty(self, shape, dtype=np.float64) -> np.ndarray:
+        """Page-locked host array (portable across the devices); freed when garbage collected."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape, dtype=np.int64))
+        nbytes = max(count * dtype.itemsize, 1)
+        p = ctypes.c_void_p()
+        check(self._lib.bq_host_alloc(self._h0, nbytes, ctypes.byref(p)))
+        buf = (ctypes.c_char * nbytes).from_address(int(p.value))
+        arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        weakref.finalize(buf, MultiEngine._free_pinned, weakref.ref(self), int(p.value))
+        return arr
+
+    @staticmethod
+    def _free_pinned(self_ref, ptr: int) -> None:
+        self = self_ref()
+        if self is None or not self._finalizer.alive:
+            return
+        self._lib.bq_host_free(self._h0, ctypes.c_void_p(ptr))
+
+    @staticmethod
+    def _mode(shard: str) -> int:
+        try:
+            return {"frames": _lib.BQ_SHARD_FRAMES, "grid": _lib.BQ_SHARD_GRID}[shard]
+        except KeyError:
+            raise ValueError("shard must be 'frames' or 'grid'") from None
+
+    def state_to_wigner(self, psi, traced: Sequence[int], xvec, yvec=None, g: float = math.sqrt(2),
+                        method: str = "clenshaw", shard: str = "frames", return_rho: bool = False, out=None):
+        """``Engine.state_to_wigner`` over all GPUs: ``psi`` (dim,) or (frames, dim) -> W [, rho]."""
+        code = method_code(method)
+        if code == METHODS["fft"]:
+            raise BQError(_lib.BQ_ERR_UNSUPPORTED, "method 'fft' is not sharded: use Engine.state_to_wigner")
+        psi = _c128(psi)
+        single = psi.ndim == 1
+        psi2 = psi.reshape(1, -1) if single else psi
+        batch, dim = psi2.shape
+        n = _n_qubits(dim)
+        traced = list(traced)
+        xvec = _f64(xvec).reshape(-1)
+        yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
+        shape = (batch, len(yvec), len(xvec))
+        if out is None:
+            out = self.pinned_empty(shape, np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape / dtype / layout")
+        D = 1 << max(n - len(traced), 0)
+        rho = np.empty((batch, D, D), dtype=np.complex128) if return_rho else None
+        check(self._lib.bq_state_to_wigner_sharded_host(
+            self._m, _ptr(psi2), n, _int_array(traced), len(traced), batch, dim, _ptr(xvec), len(xvec), _ptr(yvec), len(yvec),
+            float(g), code, self._mode(shard), _ptr(out), _ptr(rho) if return_rho else None))
+        W = out[0] if single else out
+        return (W, (rho[0] if single else rho)) if return_rho else W
+
+    def wigner(self, rho, xvec, yvec=None, g: float = math.sqrt(2), method: str = "clenshaw", shard: str = "frames", out=None):
+        """``Engine.wigner`` over all GPUs: ``rho`` (N, N) or (batch, N, N) -> W."""
+        code = method_code(method)
+        if code == METHODS["fft"]:
+            raise BQError(_lib.BQ_ERR_UNSUPPORTED, "method 'fft' is not sharded: use Engine.wigner")
+        rho = _c128(rho)
+        single = rho.ndim == 2
+        rho3 = rho.reshape(1, *rho.shape) if single else rho
+        if rho3.ndim != 3 or rho3.shape[1] != rho3.shape[2]:
+            raise TypeError("Input state is not a valid operator.")
+        batch, N, _ = rho3.shape
+        xvec = _f64(xvec).reshape(-1)
+        yvec = xvec if yvec is None else _f64(yvec).reshape(-1)
+        shape = (batch, len(yvec), len(xvec))
+        if out is None:
+            out = self.pinned_empty(shape, np.float64)
+        elif out.shape != shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape / dtype / layout")
+        check(self._lib.bq_wigner_sharded_host(self._m, _ptr(rho3), N, N, N * N, batch, _ptr(xvec), len(xvec), _ptr(yvec),
+                                               len(yvec), float(g), code, self._mode(shard), _ptr(out)))
+        return out[0] if single else out
+
+
+_multi_engines: dict[tuple, MultiEngine] = {}
+
+
+def get_multi_engine(devices: Sequence[int] | None = None) -> MultiEngine:
+    """Process-wide ``MultiEngine`` over ``devices`` (None: every visible GPU).  Raises without a GPU."""
+    key = tuple(int(d) for d in devices) if devices is not None else ("all",)
+    with _engines_lock:
+        me = _multi_engines.get(key)
+        if me is None:
+            me = MultiEngine(devices)
+            _multi_engines[key] = me
+        return me
+
+
+def device_count() -> int:
+    """CUDA devices the library sees (0 without a driver / GPU)."""
+    n = ctypes.c_int()
+    rc = _lib.load().bq_device_count(ctypes.byref(n))
+    return int(n.value) if rc == 0 else 0
+
+
 _engines: dict[int, Engine] = {}
 _engines_lock = threading.Lock()
 
@@ -562,4 +811,4 @@ def get_engine(device: int | None = None) -> Engine:
         return eng
 
 
-__all__ = ["Engine", "get_engine", "BQError", "method_code", "METHODS"]
+__all__ = ["Engine", "MultiEngine", "get_engine", "get_multi_engine", "device_count", "BQError", "method_code", "METHODS"]

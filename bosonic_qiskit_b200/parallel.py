@@ -20,6 +20,7 @@ torch is used for device memory, streams and the process group only.
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Sequence
 
 import numpy as np
@@ -169,16 +170,28 @@ def _shared_units_reduce(eng, rho_t, x_t, xvec, g, method, rank, world, dst, gro
     total = eng.grid_units(S)
     first, last = shard_range(total, rank, world)
     W = torch.zeros((S, S), dtype=torch.float64, device=rho_t.device)
-    ok = 1
+    # Every rank reaches the agreement all_reduce below whatever happens on it: 1 = share evaluated, 0 = this grid /
+    # cutoff cannot take the path (all ranks then shard by row slab), -1 = a real failure (out of memory, a CUDA
+    # error, a bad range) -- re-raised here and reported as a matching error on the other ranks instead of leaving
+    # them waiting in the collective.
+    ok, failure = 1, None
     try:
         eng.wigner_t(rho_t, x_t, g=g, method=method, out=W.unsqueeze(0), unit_range=(first, last - first))
     except BQError as exc:
-        if exc.code != BQ_ERR_UNSUPPORTED:
-            raise
-        ok = 0
+        if exc.code == BQ_ERR_UNSUPPORTED:
+            ok = 0
+        else:
+            ok, failure = -1, exc
+    except Exception as exc:  # noqa: BLE001 - anything else must not desynchronise the ranks either
+        ok, failure = -1, exc
     flag = torch.tensor([ok], device=rho_t.device)
     _dist().all_reduce(flag, op=_dist().ReduceOp.MIN, group=group)
-    if int(flag.item()) == 0:
+    verdict = int(flag.item())
+    if failure is not None:
+        raise failure
+    if verdict < 0:
+        raise RuntimeError("a peer rank failed while evaluating its share of the grid (see that rank's error)")
+    if verdict == 0:
         return False, None
     _dist().reduce(W, dst=dst, op=_dist().ReduceOp.SUM, group=group)
     return True, (W if rank == dst else None)
@@ -217,6 +230,8 @@ class PeerGatherBuffer:
         if self.rank == dst:
             nbytes = int(np.prod(self.shape, dtype=np.int64)) * 8
             self._owned = engine.device_alloc(nbytes)  # whole cudaMalloc allocation: IPC-exportable at offset 0
+            # safety net: a buffer that is dropped without free() gives its memory back when it is collected
+            self._finalizer = weakref.finalize(self, PeerGatherBuffer._release, weakref.ref(engine), self._owned)
             self.tensor = torch.as_tensor(_RawCudaArray(self._owned, self.shape, self), device=torch.device("cuda", engine.device))
             payload = [engine.ipc_export(self._owned)]
         if self.world > 1:
@@ -248,20 +263,37 @@ class PeerGatherBuffer:
     def free(self):
         if self._owned is not None:
             self.tensor = None
+            self._finalizer.detach()
             self.engine.device_free(self._owned)
             self._owned = None
 
+    @staticmethod
+    def _release(engine_ref, ptr):
+        eng = engine_ref()
+        if eng is not None:
+            try:
+                eng.device_free(ptr)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+
 
 def _peer_store_frames(eng, psi_t, traced, x_t, g, method, F, S, lo, hi, rank, world, dst, group):
+    """Frames through a CUDA-IPC gather buffer on ``dst``.  The buffer lives for this call only: the result is handed
+    back as a torch-owned copy on ``dst`` and the raw allocation is freed once every peer has unmapped it."""
     buf = PeerGatherBuffer(eng, (F, S, S), dst=dst, group=group)
+    result = None
     try:
         if hi > lo:
             eng.state_to_wigner_t(psi_t, traced, x_t, g=g, method=method, out=buf.ptr_for(lo))
         out = buf.finish()
+        if rank == dst:
+            result = out.clone()
     finally:
-        if rank != dst:
-            buf.close()
-    return out
+        buf.close()
+        if world > 1:
+            _dist().barrier(group=group)  # every peer has unmapped the buffer before its owner frees it
+        buf.free()
+    return result
 
 
 __all__ = ["shard_range", "shard_sizes", "frames_to_wigner_sharded", "wigner_row_slabs", "PeerGatherBuffer"]

@@ -81,6 +81,20 @@ def cv_partial_trace(circuit, state_vector, qubits):
     return partial_trace(state_vector, indices)
 
 
+def mean_trace_out_qubits(circuit, state_vectors, weights=None):
+    """Shot-averaged reduced density matrix of the qumodes: ``sum_k w_k trace_out_qubits(circuit, psi_k)`` over the
+    per-shot statevectors ``simulate(..., per_shot_state_vector=True)`` returns (``util.py:523-532``), the quantity
+    ``tutorials/bosonic-kitten-code`` cell 14 builds with a Python loop over shots.  One batched partial-trace launch
+    with the accumulation fused into its reduction (``bq_partial_trace_sv_accumulate_host``); ``weights=None`` is the
+    plain mean.  Returns a ``DensityMatrix`` -- the mixed-state input of ``wigner.wigner`` under noise."""
+    indices = _find_qubit_indices(circuit)
+    psi = np.stack([np.asarray(getattr(sv, "data", sv), dtype=np.complex128).reshape(-1) for sv in state_vectors])
+    n = int(psi.shape[1]).bit_length() - 1
+    _validate_qargs(indices, n)
+    rho = get_engine().partial_trace_sv_mean(psi, indices, weights)
+    return DensityMatrix(rho, dims=(2,) * (n - len(indices)))
+
+
 def avg_photon_num(circuit, state, decimals: int = 2) -> list[float]:
     """Average photon number of each qumode (``util.py:672-696``).
 
@@ -139,6 +153,7 @@ __all__ = [
     "trace_out_qumodes",
     "trace_out_qubits",
     "cv_partial_trace",
+    "mean_trace_out_qubits",
     "avg_photon_num",
     "qumode_avg_photon_num",
     "DensityMatrix",

@@ -112,16 +112,46 @@ def simulate_wigner_multiple_statevectors(
     return [W[k] for k in range(W.shape[0])]
 
 
+# A frame loop goes to every visible GPU (one process, ``MultiEngine``) once it has at least this many frames per GPU
+# -- below that one GPU finishes before the other devices' worker threads have copied their inputs in.
+MULTI_GPU_MIN_FRAMES_PER_DEVICE = 4
+# ... and ONE grid is shared out over the GPUs from this much Clenshaw work (flops) on: cutoff 1024 on 4096 x 4096 is
+# 9e13 (0.4 s on one GPU), cutoff 64 on 1024 x 1024 is 2e10 (0.15 ms: not worth a second device).
+MULTI_GPU_MIN_GRID_FLOPS = 5e12
+
+
+def _frame_devices(devices, n_frames: int):
+    """Devices a frame loop runs on: ``devices`` as given, or (None) every visible GPU when there are enough frames."""
+    from .engine import device_count
+
+    if devices is None:
+        n = device_count()
+        if n > 1 and n_frames >= MULTI_GPU_MIN_FRAMES_PER_DEVICE * n:
+            return list(range(n))
+        return None
+    devices = [int(d) for d in devices]
+    return devices if len(devices) > 1 else None
+
+
 def frames_to_wigner(frames, traced: Sequence[int], xvec, g: float = _SQRT2, method: WignerMethods = "clenshaw",
-                     out=None) -> np.ndarray:
+                     out=None, devices=None) -> np.ndarray:
     """Batched body of the reference's frame loops: (F, 2**n) statevectors -> (F, S, S) Wigner grids.
 
     Replaces ``for num in range(num_statevectors): trace_out_qubits(...); _wigner(...)``
-    (``wigner.py:92-96``, ``animate.py:326-352``) with one call of ``bq_state_to_wigner_host``.
+    (``wigner.py:92-96``, ``animate.py:326-352``) and the ``multiprocessing.Pool`` fan-out of
+    ``animate.py:191-206`` with one call: ``bq_state_to_wigner_host`` on one GPU, or -- ``devices=None`` with several
+    GPUs visible and enough frames, or an explicit list of devices -- ``bq_state_to_wigner_sharded_host``, which splits
+    the frames over the GPUs from this one process and lets each GPU write its grids into its slice of the result.
     """
     psi = np.ascontiguousarray(np.stack([np.asarray(f, dtype=np.complex128).reshape(-1) for f in frames]))
     xvec = np.asarray(xvec, dtype=np.float64)
-    return get_engine().state_to_wigner(psi, list(traced), xvec, None, g=g, method=method, out=out)
+    devs = None if _check_fft(method) else _frame_devices(devices, psi.shape[0])
+    if devs is not None:
+        from .engine import get_multi_engine
+
+        return get_multi_engine(devs).state_to_wigner(psi, list(traced), xvec, None, g=g, method=method, out=out)
+    eng = get_engine(None if not devices else int(list(devices)[0]))
+    return eng.state_to_wigner(psi, list(traced), xvec, None, g=g, method=method, out=out)
 
 
 def wigner(
@@ -175,6 +205,16 @@ def _wigner(state, xvec, yvec=None, g: float = _SQRT2, method: WignerMethods = "
 
     if rho.ndim == 1:  # qutip turns kets into density matrices
         rho = np.outer(rho, rho.conj())
+    if not _check_fft(method) and rho.ndim == 2:
+        from .engine import device_count
+
+        N, S = rho.shape[0], len(xvec)
+        if 5.0 * N * N * S * len(yvec) >= MULTI_GPU_MIN_GRID_FLOPS and device_count() > 1:
+            from .engine import get_multi_engine
+
+            # one huge grid: shared out over every GPU of the box (unit ranges / row slabs), assembled on the host
+            return get_multi_engine().wigner(rho, np.asarray(xvec, dtype=np.float64), np.asarray(yvec, dtype=np.float64),
+                                             g=g, method=method, shard="grid")
     return get_engine().wigner(rho, np.asarray(xvec, dtype=np.float64), np.asarray(yvec, dtype=np.float64), g=g,
                                method=method)
 
@@ -192,17 +232,84 @@ def plot_wigner(
     dpi: int = 100,
     **wigner_kwargs,
 ):
-    """Wigner function of ``state_vector`` (traced to the qumodes by default) handed to the
-    reference's matplotlib ``plot`` (``wigner.py:193-244``).  Rendering stays on the host and is the
-    reference's own code; only the trace + Wigner stages run on the GPU."""
+    """Wigner function of ``state_vector`` (traced to the qumodes by default) handed to ``plot``
+    (``wigner.py:193-244``).  Rendering stays on the host (matplotlib); the trace + Wigner stages run on the GPU."""
     state = trace_out_qubits(circuit, state_vector) if trace else DensityMatrix(state_vector)
     w_fock = wigner(state=state, axes_min=axes_min, axes_max=axes_max, axes_steps=axes_steps, **wigner_kwargs)
-    try:
-        from bosonic_qiskit.wigner import plot  # reference plotting, unchanged
-    except Exception as exc:  # pragma: no cover - needs matplotlib + qiskit
-        raise RuntimeError("plotting needs the reference package `bosonic_qiskit` and matplotlib") from exc
     plot(data=w_fock, axes_min=axes_min, axes_max=axes_max, axes_steps=axes_steps, file=file, num_colors=num_colors,
          draw_grid=draw_grid, dpi=dpi)
+
+
+def _pyplot():
+    try:
+        import matplotlib.pyplot as plt
+        import matplotlib.ticker as tick
+    except Exception as exc:  # pragma: no cover - matplotlib is a rendering dependency only
+        raise RuntimeError("plotting needs matplotlib (rendering is host-side; only trace + Wigner run on the GPU)") from exc
+    return plt, tick
+
+
+def plot(data, axes_min: int = -6, axes_max: int = 6, axes_steps: int = 200, file=None, num_colors: int = 100,
+         draw_grid: bool = False, dpi: int = 100):
+    """Contour plot of a Wigner grid (``wigner.py:247-287``): symmetric colour levels
+    ``linspace(-A, A, num_colors)``, ``A = max(amax, |amin|)`` (1 for an all-zero grid), ``contourf(..., cmap="RdBu")``,
+    colour bar labelled W(x,p).  Host-side matplotlib, as in the reference."""
+    plt, tick = _pyplot()
+    axis = np.linspace(axes_min, axes_max, axes_steps)
+    hi, lo = np.amax(data), np.amin(data)
+    if hi == 0 and lo == 0:
+        hi, lo = 1, -1
+    bound = max(hi, abs(lo))
+    levels = np.linspace(-bound, bound, num_colors)
+    fig, ax = plt.subplots(constrained_layout=True)
+    filled = ax.contourf(axis, axis, data, levels, cmap="RdBu")
+    ax.set_xlabel(r"$x$")
+    ax.set_ylabel(r"$p$")
+    ax.set_aspect("equal", "box")
+    if draw_grid:
+        ax.grid()
+    bar = fig.colorbar(filled, ax=ax, format=tick.FormatStrFormatter("%.2f"))
+    bar.set_label(r"$W(x,p)$", rotation=270, labelpad=25)
+    if file:
+        plt.savefig(file, dpi=dpi)
+    else:
+        plt.show()
+
+
+def snapshot_wigners(circuit, result, trace: bool = True, axes_min: int = -6, axes_max: int = 6, axes_steps: int = 200,
+                     **wigner_kwargs):
+    """The Wigner grids of every ``cv_snapshot_{k}`` statevector of a result, as ONE batched trace -> Wigner call
+    (the loop body of ``plot_wigner_snapshot``, ``wigner.py:378-410``, is one more frame loop).  Returns
+    ``[(label, W), ...]``."""
+    data = result.data()
+    labels = [f"cv_snapshot_{k}" for k in range(circuit.cv_snapshot_id)]
+    if not labels:
+        return []
+    frames = [np.asarray(getattr(data[label], "data", data[label])) for label in labels]
+    method = wigner_kwargs.pop("method", "clenshaw")
+    g = wigner_kwargs.pop("g", _SQRT2)
+    if wigner_kwargs:
+        raise TypeError(f"wigner() got an unexpected keyword argument {next(iter(wigner_kwargs))!r}")
+    xvec = np.linspace(axes_min, axes_max, axes_steps)
+    traced = _find_qubit_indices(circuit) if trace else []
+    W = frames_to_wigner(frames, traced, xvec, g=g, method=method)
+    if _check_fft(method):
+        W, yvec = W
+        return [(label, (W[k], yvec)) for k, label in enumerate(labels)]
+    return [(label, W[k]) for k, label in enumerate(labels)]
+
+
+def plot_wigner_snapshot(circuit, result, folder=None, trace: bool = True, axes_min: int = -6, axes_max: int = 6,
+                         axes_steps: int = 200, num_colors: int = 100, **wigner_kwargs):
+    """One PNG per ``cv_snapshot_{k}`` of ``result`` (``wigner.py:378-410``): the grids come from one batched GPU
+    call (``snapshot_wigners``), each is then drawn by ``plot``."""
+    from pathlib import Path
+
+    for label, w_fock in snapshot_wigners(circuit, result, trace, axes_min, axes_max, axes_steps, **wigner_kwargs):
+        file = Path(folder) / f"{label}.png" if folder else f"{label}.png"
+        if isinstance(w_fock, tuple):  # method="fft": (W, yvec)
+            w_fock = w_fock[0]
+        plot(data=w_fock, axes_min=axes_min, axes_max=axes_max, axes_steps=axes_steps, file=file, num_colors=num_colors)
 
 
 def wigner_projections(circuit, x, y_z, y_x, xvec=None, **wigner_kwargs):
@@ -243,6 +350,21 @@ def wigner_projections(circuit, x, y_z, y_x, xvec=None, **wigner_kwargs):
     return W[0], W[1], W[2], W[3]
 
 
+def _add_contourf(ax, fig, title, x, y, z, draw_grid: bool = False):
+    """One panel of ``plot_wigner_projection`` (``wigner.py:413-444``): symmetric colour levels from the panel's own
+    extremes (at least 1e-4 wide), integer axis ticks."""
+    bound = max(np.amax(z), abs(np.amin(z)), 0.0001)
+    filled = ax.contourf(x, y, z, np.linspace(-bound, bound, 100), cmap="RdBu")
+    ax.set_xlabel("x")
+    ax.set_xticks(sorted({int(v) for v in x}))
+    ax.set_ylabel("p")
+    ax.set_yticks(sorted({int(v) for v in y}))
+    if draw_grid:
+        ax.grid()
+    ax.set_title(title)
+    fig.colorbar(filled, ax=ax)
+
+
 def plot_wigner_projection(circuit, qubit, file=None, draw_grid: bool = False, **wigner_kwargs):
     """Plot the projections onto 0, 1, +, - of a one-qubit CVCircuit (``wigner.py:290-375``).
 
@@ -257,11 +379,7 @@ def plot_wigner_projection(circuit, qubit, file=None, draw_grid: bool = False, *
     circuit.data.pop()
     xvec = np.linspace(-6, 6, 200)
     w0, w1, wp, wm = wigner_projections(circuit, x, y_z, y_x, xvec, **wigner_kwargs)
-    try:
-        import matplotlib.pyplot as plt
-        from bosonic_qiskit.wigner import _add_contourf  # reference plotting helper, unchanged
-    except Exception as exc:  # pragma: no cover - needs matplotlib + the reference package
-        raise RuntimeError("plotting needs the reference package `bosonic_qiskit` and matplotlib") from exc
+    plt, _ = _pyplot()
     fig, ((ax0, ax1), (ax2, ax3)) = plt.subplots(2, 2, figsize=(12.8, 12.8))
     _add_contourf(ax0, fig, "Projection onto zero", xvec, xvec, w0, draw_grid)
     _add_contourf(ax1, fig, "Projection onto one", xvec, xvec, w1, draw_grid)
@@ -284,5 +402,8 @@ __all__ = [
     "wigner",
     "wigner_mle",
     "_wigner",
+    "plot",
     "plot_wigner",
+    "plot_wigner_snapshot",
+    "snapshot_wigners",
 ]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BQ_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+#define BQ_B200_VERSION 200 /* major*10000 + minor*100 + patch */
 
 typedef enum bq_status {
     BQ_OK = 0,
@@ -92,6 +92,18 @@ int bq_partial_trace_sv_multi_host(bq_handle_t h, const double *psi, int n_qubit
 int bq_partial_trace_sv_multi_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced,
                                   int n_traced, int n_sets, double *d_rho_out, void *stream);
 
+/* Shot-averaged reduced density matrix: rho = sum_k w_k Tr_traced |psi_k><psi_k| over `shots` statevectors of ONE
+ * circuit, in one batched launch of the tensor-core contraction with the accumulation over shots fused into its
+ * split reduction.  Replaces the Python loop that calls trace_out_qubits per shot and averages the results over the
+ * per-shot statevectors simulate() collects (src/bosonic_qiskit/util.py:523-532;
+ * tutorials/bosonic-kitten-code/bosonic-kitten-code.ipynb cell 14) -- the mixed-state input of the Wigner routine
+ * under noise.  weights: `shots` doubles, or NULL for the plain mean (w_k = 1 / shots).  rho_out: D x D.          */
+int bq_partial_trace_sv_accumulate_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                        int shots, int64_t psi_stride, const double *weights, double *rho_out);
+int bq_partial_trace_sv_accumulate_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                                       int shots, int64_t psi_stride, const double *d_weights, double *d_rho_out,
+                                       void *stream);
+
 /* DensityMatrix branch: rho_keep[i,j] = sum_t rho[(i,t),(j,t)]  (reached through
  * cv_partial_trace / avg_photon_num with a DensityMatrix, src/bosonic_qiskit/util.py:619,693).  */
 int bq_partial_trace_dm_host(bq_handle_t h, const double *rho, int n_qubits, const int *traced, int n_traced,
@@ -138,6 +150,17 @@ int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, con
                            int batch, int64_t psi_stride, const double *d_xvec, int nx, const double *d_yvec,
                            int ny, double g, int method, double *d_W_out, double *d_rho_out, void *stream);
 
+/* Several traces of ONE statevector, each followed by its Wigner grid, in one call: per-site reduced density
+ * matrices + per-site Wigner functions (the per-qumode loop of src/bosonic_qiskit/util.py:688-694 followed by
+ * wigner.py:190 per site; BASELINE config 4).  `traced` holds n_sets lists of n_traced positions; W_out is
+ * n_sets x ny x nx, rho_out (optional) n_sets x D x D.  One kernel launch when the traces are small.             */
+int bq_state_to_wigner_multi_host(bq_handle_t h, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                  int n_sets, const double *xvec, int nx, const double *yvec, int ny, double g,
+                                  int method, double *W_out, double *rho_out);
+int bq_state_to_wigner_multi_dev(bq_handle_t h, const double *d_psi, int n_qubits, const int *traced, int n_traced,
+                                 int n_sets, const double *d_xvec, int nx, const double *d_yvec, int ny, double g,
+                                 int method, double *d_W_out, double *d_rho_out, void *stream);
+
 /* per-frame (min, max) of a finished batch of grids: the colour-scale reduction of
  * animate._animate (src/bosonic_qiskit/animate.py:265-311).  out[2*b] = min, out[2*b+1] = max.    */
 int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame, int batch, double *d_out,
@@ -166,6 +189,11 @@ int bq_profile_enable(bq_handle_t h, int on);
  * carries it, overridable with the environment variable BQ_B200_SASS=plain), mode 0 = exactly what nvcc
  * scheduled.  Results are bit-identical.  *active (may be NULL) receives the mode in effect.            */
 int bq_set_sass_mode(bq_handle_t h, int mode, int *active);
+/* Result of the load-time self-check of the re-scheduled SASS: when the first handle on a device is created, every
+ * patched kernel variant and its nvcc-scheduled twin evaluate the same probe grids and are compared bit for bit
+ * (environment BQ_B200_SASS_VERIFY=0 skips it).  *bad_mask: bit v set = variant v differed (it runs nvcc's schedule
+ * from then on); *checked: variants compared.  Either pointer may be NULL.                                        */
+int bq_sass_self_check(bq_handle_t h, uint64_t *bad_mask, int *checked);
 int bq_profile_read(bq_handle_t h, double *total_ms, int *launches);
 
 /* ---- mirror-symmetric grids ------------------------------------------------------------------
@@ -195,6 +223,38 @@ int bq_set_sym_variant(bq_handle_t h, int variant);
 int bq_last_wigner_variant(bq_handle_t h, int *variant);
 /* 1 if nx == ny >= 2, yvec[i] == xvec[i] and |xvec[i] + xvec[nx-1-i]| <= 4 ulp of max|xvec|; else 0 */
 int bq_grid_is_mirror(const double *xvec, int nx, const double *yvec, int ny);
+
+/* ---- several GPUs from ONE process ------------------------------------------------------------
+ * The reference fans its frame loop out from inside a plain function call (multiprocessing.Pool.starmap over
+ * frames, src/bosonic_qiskit/animate.py:166-169,191-206; the sequential loops at wigner.py:92-96 and
+ * animate.py:326-352).  A bq_multi_t owns one handle + one worker thread per GPU of the box; the sharded entry
+ * points take HOST pointers like the `_host` entry points and return when W_out is complete.  No collective on
+ * the data path:
+ *   BQ_SHARD_FRAMES  contiguous frame blocks per GPU, every GPU copies its finished grids straight into its slice
+ *                    of W_out over its own PCIe link (page-locked W_out, e.g. from bq_host_alloc, makes those
+ *                    copies concurrent);
+ *   BQ_SHARD_GRID    ONE grid (batch == 1): a mirror-symmetric grid is shared out by equal unit ranges, every GPU
+ *                    stores its points into one frame buffer on the first GPU through NVLink peer memory, one copy
+ *                    to the host; any other grid by row slabs.
+ * bq_multi_init: devs == NULL / n_dev <= 0 takes every visible GPU (n_dev > 0 with devs == NULL: the first n_dev);
+ * a device listed more than once takes that many shares.                                                          */
+typedef struct bq_multi_s *bq_multi_t;
+enum { BQ_SHARD_FRAMES = 0, BQ_SHARD_GRID = 1 };
+int bq_multi_init(bq_multi_t *out, int n_dev, const int *devs);
+int bq_multi_finalize(bq_multi_t m);
+int bq_multi_device_count(bq_multi_t m, int *count);
+/* the per-device handle (index < device count), e.g. for bq_set_sass_mode / bq_profile_enable; owned by `m` */
+int bq_multi_handle(bq_multi_t m, int index, bq_handle_t *out);
+/* kernels launched by all of m's handles since creation */
+int bq_multi_launch_count(bq_multi_t m, uint64_t *count);
+/* sharded bq_state_to_wigner_host (frame loops of wigner.py:92-96, animate.py:191-206,326-352) */
+int bq_state_to_wigner_sharded_host(bq_multi_t m, const double *psi, int n_qubits, const int *traced, int n_traced,
+                                    int batch, int64_t psi_stride, const double *xvec, int nx, const double *yvec,
+                                    int ny, double g, int method, int shard_mode, double *W_out, double *rho_out);
+/* sharded bq_wigner_host (qutip.wigner per frame, wigner.py:190) */
+int bq_wigner_sharded_host(bq_multi_t m, const double *rho, int N, int64_t ld, int64_t rho_stride, int batch,
+                           const double *xvec, int nx, const double *yvec, int ny, double g, int method, int shard_mode,
+                           double *W_out);
 
 /* ---- CUDA IPC plumbing for the multi-GPU tile gather ---------------------------------------- */
 /* One process per GPU: the root exports its gather buffer, peers open it and let the Wigner

@@ -22,7 +22,7 @@ def test_library_builds_and_loads():
     path = _build.build_library()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.bq_version() == 100
+    assert lib.bq_version() == 200
 
 
 def test_every_declared_symbol_is_exported_and_bound():
