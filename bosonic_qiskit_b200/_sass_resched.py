@@ -27,7 +27,9 @@ Hazards the emitted code keeps guarded (each one was a fault or a wrong result o
     of the stationary side between FP64 uses, and an FP64 value carried in over the back edge that is last read
     before the stationary side redefines the register (ptxas's software-pipelined loops);
   * a wait for load data on a stationary instruction is only accepted after the last DFMA (the closing branch), where
-    the last DFMA of the new order already waits for every load in flight.
+    the last DFMA of the new order already waits for every load in flight;
+  * an instruction that sets a scoreboard barrier keeps a stall count of at least 2 when the next instruction waits
+    on that barrier (the barrier is not visible earlier).
 
 usage: python -m bosonic_qiskit_b200._sass_resched in.cubin out.cubin [--min-dfma 24] [--max-regs 128] [--verbose]
 """
@@ -719,6 +721,17 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
             mask |= 1 << bar_of[p]
         k_last = dslots[-1]
         words[k_last] = set_ctl(words[k_last], wait=((words[k_last] >> 116) & 0x3F) | mask)
+
+    # A scoreboard barrier becomes visible one cycle after the instruction that sets it has issued: when the NEXT
+    # instruction waits on it, the setter needs a stall count of at least 2 (ptxas never emits less: 0 of 1328 such
+    # pairs in this file's unpatched image; maxas documents the same rule).  With a stall of 1 the wait falls through --
+    # harmless most of the time, but a DFMA that lands in a load's address register then overtakes a load held up in
+    # the memory queue: an illegal-address fault that came and went with host-side timing.
+    for k in range(n - 1):
+        sets = ({(words[k] >> 110) & 7, (words[k] >> 113) & 7} - {7})
+        if any((words[k + 1] >> 116) & 0x3F & (1 << b) for b in sets) and (words[k] >> 105) & 0xF < 2:
+            words[k] = set_ctl(words[k], stall=2)
+            bumped += 1
 
     for (ka, oa, ra), (kb, ob, rb) in zip(emitted, emitted[1:]):
         dst_a = {assign[oa], assign[oa] + 1}

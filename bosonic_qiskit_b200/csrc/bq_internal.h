@@ -8,12 +8,21 @@ namespace bq {
 
 constexpr int kResidentMaxN = 64;  // stream fits twice per SM in shared memory up to this cutoff
 constexpr int kMaxQubits = 40;
-constexpr int kKernelSlots = 48;
+constexpr int kKernelSlots = 64;
 
 // records in the coefficient stream of cutoff N, and the first record of the diagonal with K = N-L
 // coefficients (K >= 2); layout described in bq_common.cuh
 __host__ __device__ inline int64_t stream_records(int N) { return (int64_t)N * (N + 1) / 2 + N - 1; }
 __host__ __device__ inline int64_t diag_pos(int K) { return ((int64_t)K * K + K - 4) / 2; }
+
+// Whether a mirror-symmetric grid of `units` units (all frames of the launch) runs on the recurrence-sharing
+// kernels: always for the resident cutoffs, for the ring kernels only when there are enough units to fill the GPU
+// (below that the point-by-point kernels finish first).  One rule for the single-GPU launcher and for the
+// multi-GPU unit-range sharding, so that both evaluate a given grid with the same kernels (bit-identical results).
+inline bool sym_kernels_cover(int N, int64_t units, int sm_count)
+{
+    return N <= kResidentMaxN || units >= 2LL * 256 * (sm_count / 2);
+}
 
 struct DeviceInfo {
     int device = 0;
@@ -23,6 +32,8 @@ struct DeviceInfo {
     int pts8 = 0;       // use the 8-points-per-thread resident kernel for large grids
     int sym_force = -1; // >= 0: tuning aid (env BQ_B200_SYM_VARIANT), only this symmetric-kernel variant is eligible
     int sym_split_main = -1, sym_split_tail = -1;  // tuning aid (env BQ_B200_SYM_SPLIT=main:tail): whole rounds / remainder
+    int sym_phase = 1;  // symmetric kernels: stagger the warps of a scheduler (env BQ_B200_SYM_PHASE=0 turns it off)
+    int sym_delay = 0;  // parked ring kernel: warp w starts a tile w * sym_delay cycles late (env BQ_B200_SYM_DELAY)
     int last_variant = -1;  // variant id (kKernelNames index) of the last Wigner kernel launched
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     uint64_t patched_bad = 0;  // bit v: the patched image of variant v failed the load-time self-check -> nvcc's schedule
@@ -63,7 +74,7 @@ struct WigParams {
     int pro_n_keep, pro_n_trace, pro_psi_batch;
     double2 *pro_rho_out;             // mode 2, optional: [batch][N][N]
     // mirror-symmetric grids (wigner_sym_* kernels): U = ceil(S/2) mirror classes, U(U+1)/2 units per frame
-    int sym, sym_U;
+    int sym, sym_U, sym_phase, sym_delay;
     int64_t sym_units;  // units this launch evaluates per frame ...
     int64_t sym_first;  // ... starting at this unit (a rank's share of one large grid; 0 = the whole grid)
     int64_t sym_want_first, sym_want_count;  // caller's unit range (count < 0: all)

@@ -163,7 +163,10 @@ int one_grid(bq_multi_s *m, const double *rho, int N, int64_t ld, const double *
     const size_t n_dev = m->devices.size();
     const bool mirror = bq_grid_is_mirror(xvec, nx, yvec, ny) != 0;
     const int64_t units = bq_grid_units(nx);
-    const bool by_units = mirror && m->peer_ok && N >= 2;
+    int sm_count = 0;
+    CUM(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, m->devices[0]));
+    // unit ranges only where ONE GPU would run the recurrence-sharing kernels on this grid too: same kernels, same bits
+    const bool by_units = mirror && m->peer_ok && N >= 2 && bq::sym_kernels_cover(N, units, sm_count);
     const size_t in_bytes = psi ? sizeof(double) * 2 * ((size_t)1 << n_qubits) : sizeof(double) * 2 * ((size_t)(N - 1) * ld + N);
     const size_t frame_bytes = sizeof(double) * (size_t)nx * ny;
     std::vector<int> traced_v(traced, traced + (psi ? n_traced : 0));

@@ -16,6 +16,8 @@
 //     (1-D TMA) + mbarrier full/empty pairs, one elected producer thread, every warp a consumer;
 //   * persistent CTAs take tiles from a global counter so that all 148 SMs finish together;
 //   * stores are 32 B per thread, 1 KiB contiguous per warp, streaming (evict-first).
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -668,7 +670,7 @@ __device__ __forceinline__ void sym_tail(SymPoints<CL> &s, const double4 t)
 // the steps of one diagonal (everything but its tail); returns the tail record
 template <int CL, typename P>
 __device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__restrict__ cd,
-                                                      const double4 *__restrict__ td, const int K)
+                                                      const double4 *__restrict__ td, const int K, const int lead = 0)
 {
     {
         const double2 c1 = cd[0], c0 = cd[1];
@@ -684,6 +686,12 @@ __device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__res
     const double4 *tp = td + 2;
     const int m = K - 2;
     int r = 0;
+    // Staggered warps: the trip below opens with its coefficient loads (~60 cycles before the first DFMA can issue)
+    // and the two warps of a scheduler, started together, reach that point together -- the fp64 pipe idles.  A warp
+    // with `lead` > 0 takes that many single steps first, so its trips open while its partner is mid-trip.
+    const int nl = min(lead, m);
+#pragma unroll 1
+    for (; r < nl; ++r) sym_step<CL>(s, cp[r], tp[r]);
     // four steps per trip: with 5 CL DFMAs per step the loop control and the load latency of a two-step body
     // showed as `wait` stalls (fp64 pipe 72 % busy at N = 256)
 #pragma unroll 1
@@ -698,11 +706,44 @@ __device__ __forceinline__ double4 sym_diagonal_steps(P &s, const double2 *__res
     return tp[m];
 }
 
+// Steps of one diagonal, EIGHT steps per trip (the 4-step remainder loop after it): half as many trip openings --
+// each one ~60 cycles of address arithmetic + shared-memory latency before the first DFMA can issue -- per step.
+template <int CL, typename P>
+__device__ __forceinline__ double4 sym_diagonal_steps8(P &s, const double2 *__restrict__ cd,
+                                                       const double4 *__restrict__ td, const int K, const int lead = 0)
+{
+    {
+        const double2 c1 = cd[0], c0 = cd[1];
+#pragma unroll
+        for (int k = 0; k < CL; ++k) {
+            s.y1r[k] = c1.x;
+            s.y1i[k] = c1.y;
+            s.y0r[k] = c0.x;
+            s.y0i[k] = c0.y;
+        }
+    }
+    const double2 *cp = cd + 2;
+    const double4 *tp = td + 2;
+    const int m = K - 2;
+    int r = 0;
+    const int nl = min(lead, m);
+#pragma unroll 1
+    for (; r < nl; ++r) sym_step<CL>(s, cp[r], tp[r]);
+#pragma unroll 1
+    for (; r + 7 < m; r += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sym_step<CL>(s, cp[r + u], tp[r + u]);
+    }
+#pragma unroll 1
+    for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
+    return tp[m];
+}
+
 template <int CL>
 __device__ __forceinline__ void sym_diagonal(SymPoints<CL> &s, const double2 *__restrict__ cd,
-                                             const double4 *__restrict__ td, const int K)
+                                             const double4 *__restrict__ td, const int K, const int lead = 0)
 {
-    const double4 t = sym_diagonal_steps<CL>(s, cd, td, K);
+    const double4 t = sym_diagonal_steps<CL>(s, cd, td, K, lead);
     sym_tail<CL>(s, t);
 }
 
@@ -728,6 +769,14 @@ __device__ __forceinline__ void sym_tail_parked(SymCore<CL> &s, const double4 t,
         // them in flight the tail, not the loop, set the kernel's register count (255 + spills)
         asm volatile("" ::: "memory");
     }
+}
+
+// single steps a warp takes ahead of its 4-step trips (see sym_diagonal_steps): warps w, w + 4, w + 8 ... share a
+// scheduler and get 0, 4/n, 2 * 4/n ... steps, n = warps per scheduler
+__device__ __forceinline__ int sym_lead(const WigParams &p, int threads)
+{
+    const int per_sched = threads >> 7;
+    return (p.sym_phase && per_sched > 1) ? (int)(threadIdx.x >> 7) * (4 / per_sched) : 0;
 }
 
 // unit index -> (a, b), a <= b < U;  row a starts at a U - a (a - 1) / 2
@@ -824,8 +873,9 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_sym_resident_kernel(cons
         const int64_t chunk = (int64_t)tif * THREADS + tid;
         sym_load<CL>(p, chunk, s, ua, ub, cs_s[0]);
         int pos = 1;
+        const int lead = sym_lead(p, THREADS);
         for (int K = 2; K <= N; ++K) {
-            sym_diagonal<CL>(s, cs_s + pos, tab_s + pos, K);
+            sym_diagonal<CL>(s, cs_s + pos, tab_s + pos, K, lead);
             pos += K + 1;
         }
         sym_store<CL>(p, frame, chunk, s, ua, ub);
@@ -902,7 +952,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
             }
             const int Kend = group_end(K, g == 0, cap, N);
             for (; K < Kend; ++K) {
-                sym_diagonal<CL>(s, cb + pos, tb + pos, K);
+                sym_diagonal<CL>(s, cb + pos, tb + pos, K, sym_lead(p, THREADS));
                 pos += K + 1;
             }
             __syncwarp();
@@ -920,8 +970,9 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
 // 5 (K - 2) DFMA), a thread holds CL = 4 units in ~140 registers: 20 DFMA per step between two rounds of
 // coefficient loads, and room for the re-scheduler's operand-reuse chains.  Two ring stages instead of three pay for
 // the 128 KB of accumulators (a stage is a whole diagonal: its refill hides behind hundreds of steps).
-template <int CL, int THREADS, int STAGES>
-__global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184) wigner_sym_diag_parked_kernel(const WigParams p)
+template <int CL, int THREADS, int STAGES, int TRIP>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : TRIP == 8 ? 224 : 184)
+    wigner_sym_diag_parked_kernel(const WigParams p)
 {
     constexpr int NWARPS = THREADS / 32;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -929,8 +980,8 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184
     double4 *tab_s = reinterpret_cast<double4 *>(smem);
     double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)STAGES * cap * 32);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * cap * 48);
-    uint64_t *empty = full + STAGES;
-    int *slot = reinterpret_cast<int *>(empty + STAGES);
+    int *slot = reinterpret_cast<int *>(full + 2 * STAGES);
+    int *done = slot + 4;  // [STAGES] warps that have finished with the stage's current contents
     const size_t acc_off = ((size_t)STAGES * cap * 48 + 2 * STAGES * 8 + 64 + 15) & ~(size_t)15;
     const int tid = threadIdx.x;
     double2 *acc = reinterpret_cast<double2 *>(smem + acc_off) + tid;
@@ -938,13 +989,13 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NWARPS);
+            done[s] = 0;
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    uint32_t full_phase = 0, fill_count = 0;
+    uint32_t full_phase = 0;
     TileCursor tc{0, 0};
     if (p.pro_mode) fused_prologue(p);
 
@@ -953,23 +1004,35 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184
         const int tif = tile - frame * p.tiles_per_frame;
         const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
 
-        int pg = 0, pK = 2;
-        auto produce = [&]() {
-            const uint32_t st = (uint32_t)pg % STAGES;
-            const int Kend = group_end(pK, pg == 0, cap, N);
-            const int64_t first = (pg == 0) ? 0 : diag_pos(pK);
+        // The ring: ALL stages are filled when the tile starts, and a stage is refilled with the next group by
+        // whichever warp is the LAST to finish with its contents -- nobody ever waits for a stage to drain, and a
+        // group's copy is in flight for as long as the groups in the other stages take to consume.  (Before: one
+        // thread refilled after its own warp's pass, waiting for the slowest warp first, and with two stages that
+        // refill was issued at the very moment its data was needed.)  Group boundaries are a pure function of the
+        // cutoff, so every warp tracks the cursor (pg, pK) of the next group to load by itself.
+        auto load_group = [&](int g, int K_first) {  // one thread
+            const uint32_t st = (uint32_t)g % STAGES;
+            const int Kend = group_end(K_first, g == 0, cap, N);
+            const int64_t first = (g == 0) ? 0 : diag_pos(K_first);
             const int64_t last = (Kend <= N) ? diag_pos(Kend) : (int64_t)p.R_tot;
             const uint32_t recs = (uint32_t)(last - first);
-            mbar_wait(&empty[st], ((fill_count >> st) & 1u) ^ 1u);
-            fill_count ^= 1u << st;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the warps' reads of the stage -> the bulk copy's writes
             mbar_arrive_expect_tx(&full[st], recs * 48u);
             bulk_g2s(tab_s + (size_t)st * cap, p.tab + first, recs * 32u, &full[st]);
             bulk_g2s(cs_s + (size_t)st * cap, cs_g + first, recs * 16u, &full[st]);
-            ++pg;
-            pK = Kend;
         };
-        if (tid == 0)
-            for (int d = 0; d < STAGES - 1 && pK <= N; ++d) produce();
+        int pg = 0, pK = 2;
+        for (; pg < STAGES && pK <= N; ++pg) {
+            if (tid == 0) load_group(pg, pK);
+            pK = group_end(pK, pg == 0, cap, N);
+        }
+        if (p.sym_delay) {
+            // staggered warps: the per-diagonal tails (16 shared-memory accesses of 16 bytes per unit) of the warps of
+            // an SM then fall under each other's DFMA work instead of all meeting at the shared-memory crossbar
+            const long long t0 = clock64(), wait = (long long)(tid >> 5) * p.sym_delay;
+            while (clock64() - t0 < wait) {
+            }
+        }
 
         SymCore<CL> s;
         int ua[CL], ub[CL];
@@ -1001,13 +1064,24 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : 184
             }
             const int Kend = group_end(K, g == 0, cap, N);
             for (; K < Kend; ++K) {
-                const double4 t = sym_diagonal_steps<CL>(s, cb + pos, tb + pos, K);
+                const double4 t = TRIP == 8 ? sym_diagonal_steps8<CL>(s, cb + pos, tb + pos, K, 2 * sym_lead(p, THREADS))
+                                            : sym_diagonal_steps<CL>(s, cb + pos, tb + pos, K, sym_lead(p, THREADS));
                 sym_tail_parked<CL, THREADS>(s, t, acc);
                 pos += K + 1;
             }
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
-            if (tid == 0 && pK <= N) produce();
+            if (pK <= N) {  // group pg (= g + STAGES) goes into the stage this warp has just finished with
+                if ((tid & 31) == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(&done[st], 1) == NWARPS - 1) {
+                        done[st] = 0;
+                        __threadfence_block();
+                        load_group(pg, pK);
+                    }
+                }
+                pK = group_end(pK, false, cap, N);
+                ++pg;
+            }
         }
         double *Wf = p.W + (int64_t)frame * p.w_stride;
         const int S = p.nx;
@@ -1164,7 +1238,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 21;
+constexpr int kVariants = 22;
 constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
@@ -1187,8 +1261,9 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq22wigner_sym_diag_kernelILi1ELi256ELi3EEEvNS_9WigParamsE",
     "_ZN2bq26wigner_sym_resident_kernelILi4ELi256ELi1EEEvNS_9WigParamsE",
     "_ZN2bq22wigner_sym_diag_kernelILi4ELi256ELi3EEEvNS_9WigParamsE",
-    "_ZN2bq29wigner_sym_diag_parked_kernelILi4ELi256ELi2EEEvNS_9WigParamsE",
-    "_ZN2bq29wigner_sym_diag_parked_kernelILi3ELi384ELi2EEEvNS_9WigParamsE",
+    "_ZN2bq29wigner_sym_diag_parked_kernelILi4ELi256ELi2ELi4EEEvNS_9WigParamsE",
+    "_ZN2bq29wigner_sym_diag_parked_kernelILi3ELi384ELi2ELi4EEEvNS_9WigParamsE",
+    "_ZN2bq29wigner_sym_diag_parked_kernelILi4ELi256ELi2ELi8EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -1310,8 +1385,9 @@ const VariantInfo kVariantInfo[kVariants] = {
     {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 4, 1, 256, kDiagStages},
     {(const void *)wigner_sym_resident_kernel<4, 256, 1>, 3, 4, 256, 0},
     {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 4, 4, 256, kDiagStages},
-    {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2>, 5, 4, 256, 2},
-    {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2>, 5, 3, 384, 2},
+    {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 4>, 5, 4, 256, 2},
+    {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2, 4>, 5, 3, 384, 2},
+    {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 8>, 5, 4, 256, 2},
 };
 
 size_t variant_smem(const VariantInfo &v, int N, int R_tot)
@@ -1406,7 +1482,10 @@ cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *che
         VCHK(cudaMalloc(&d_tab, sizeof(double4) * (size_t)R));
         VCHK(cudaMemcpyAsync(d_rho, rho.data(), sizeof(double2) * rho.size(), cudaMemcpyHostToDevice, st));
         VCHK(launch_build_tab(d_tab, N, st));
+        const char *only_env = std::getenv("BQ_B200_SASS_VERIFY_ONLY");  // bisecting aid: check this variant alone
+        const int only = only_env ? std::atoi(only_env) : -1;
         for (int v = 0; v < kVariants; ++v) {
+            if (only >= 0 && v != only) continue;
             const VariantInfo &vi = kVariantInfo[v];
             const bool resident_kind = vi.kind == 0 || vi.kind == 3;
             if (resident_kind != (N <= kResidentMaxN)) continue;
@@ -1440,6 +1519,8 @@ cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *che
                 p.sym_units = (int64_t)p.sym_U * (p.sym_U + 1) / 2;
                 p.sym_first = 0;
                 p.sym_want_count = -1;
+                p.sym_phase = dev.sym_phase;
+                p.sym_delay = dev.sym_delay;
                 dev.sass_mode = pass;  // 0: nvcc's schedule, 1: the patched image
                 VCHK(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned int) * 4, st));
                 VCHK(cudaMemsetAsync(d_W, 0xFF, sizeof(double) * Wa.size(), st));
@@ -1447,6 +1528,8 @@ cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *che
                 cudaError_t e = run(vi.plain, v, vi.threads, smem, p, vi.pts, dev, st, nullptr, sym_chunks);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(pass ? Wb.data() : Wa.data(), d_W, sizeof(double) * Wa.size(), cudaMemcpyDeviceToHost, st);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess || std::getenv("BQ_B200_SASS_VERIFY_DEBUG"))
+                    std::fprintf(stderr, "self-check: cutoff %d variant %d pass %d -> %s\n", N, v, pass, cudaGetErrorName(e));
                 if (e != cudaSuccess) {
                     cudaGetLastError();
                     if (pass == 0) {  // the plain kernel itself cannot run this probe: nothing to compare
@@ -1513,8 +1596,10 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.90},
             {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 16, 1, 256, 0.60},
             {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 18, 4, 256, 0.90},
-            {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2>, 19, 4, 256, 1.00, 2, 1},
-            {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2>, 20, 3, 384, 0.78, 2, 1},
+            {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 4>, 19, 4, 256, 1.00, 2, 1},
+            {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2, 4>, 20, 3, 384, 0.78, 2, 1},
+            // eight steps per trip: +0.9 % at cutoff 1024 (369.2 against 372.4 ms on 4096^2), -1 % at cutoff 128
+            {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 8>, 21, 4, 256, 1.00, 2, 2},
         };
         const bool resident = p.N <= kResidentMaxN;
         auto smem_of = [&](const SymVariant &v) -> size_t {
@@ -1523,7 +1608,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             return v.parked ? ((ring + 15) & ~(size_t)15) + (size_t)v.cl * 8 * v.threads * sizeof(double2) : ring;
         };
         const SymVariant *vars = resident ? resident_variants : ring_variants;
-        const int nvars = resident ? 6 : 7;
+        const int nvars = resident ? 6 : 8;
         struct Cand {
             const SymVariant *v;
             size_t smem;
@@ -1531,9 +1616,9 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             int64_t ctas, tiles;
             double round_cost;  // one round of resident CTAs: units per SM / how busy the variant keeps the fp64 pipe
         };
-        Cand cand[7];
+        Cand cand[8];
         int ncand = 0;
-        if (resident || p.sym_want_count >= 0 || units >= 2LL * 256 * (dev.sm_count / 2)) {
+        if (p.sym_want_count >= 0 || sym_kernels_cover(p.N, units, dev.sm_count)) {
             for (int i = 0; i < nvars; ++i) {
                 const SymVariant &v = vars[i];
                 const void *func = nullptr;
@@ -1547,7 +1632,9 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 // (the 2-unit tile loses ~6 % to the 3-unit one at cutoff 64 and wins ~5 % at cutoff <= 32; parked
                 // accumulators cost 16 shared-memory accesses per unit and diagonal: 0.92 of the 3-unit ring tile at
                 // cutoff 128, 0.99 at 256, 1.09 at 1024 -- profiles/r1d_sym_variants_parked.txt)
-                const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93 : v.parked ? v.eff * (1.10 - 23.0 / p.N) : v.eff;
+                const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93
+                                   : v.parked           ? v.eff * (1.10 - 23.0 / p.N) * (v.parked == 2 ? (p.N >= 512 ? 1.009 : 0.99) : 1.0)
+                                                        : v.eff;
                 Cand &c = cand[ncand++];
                 c.v = &v;
                 c.smem = smem;
@@ -1562,6 +1649,8 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             WigParams q = p;
             q.sym_first = first;
             q.sym_units = count;
+            q.sym_phase = dev.sym_phase;
+            q.sym_delay = dev.sym_delay;
             if (pro_done) q.pro_mode = 0;
             pro_done = true;
             return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, (count + v.cl - 1) / v.cl);

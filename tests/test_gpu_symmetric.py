@@ -184,7 +184,7 @@ def test_grid_verdict_follows_the_tensor_not_its_address(engine):
 
 
 RESIDENT_VARIANTS = [8, 9, 11, 12, 13, 17]
-RING_VARIANTS = [10, 14, 15, 16, 18, 19, 20]
+RING_VARIANTS = [10, 14, 15, 16, 18, 19, 20, 21]
 
 
 @pytest.mark.parametrize("variant", RESIDENT_VARIANTS + RING_VARIANTS)
