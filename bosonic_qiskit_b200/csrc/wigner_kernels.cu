@@ -223,6 +223,7 @@ __device__ __noinline__ void fused_prologue(const WigParams &p)
             if (per_thread) {
                 const uint64_t step = pro_deposit(1ull, map->trace, nt);
                 uint64_t toff = 0;
+#pragma unroll 8
                 for (int64_t t = 0; t < T; ++t) {
                     const double2 x = psi[row_i | toff], y = psi[row_j | toff];
                     re = fma(x.x, y.x, fma(x.y, y.y, re));   // x conj(y)
@@ -233,6 +234,9 @@ __device__ __noinline__ void fused_prologue(const WigParams &p)
             } else {
                 const uint64_t step = pro_deposit(32ull, map->trace, nt);
                 uint64_t toff = pro_deposit((uint64_t)lane, map->trace, nt);
+                // (unrolled: the 16 loads of eight trips are in flight together -- with 4096 traced indices per element the
+                // serial trips, each a round trip to L2, were most of a 4-site / cutoff-16 call; summation order unchanged)
+#pragma unroll 8
                 for (int64_t t = lane; t < T; t += 32) {
                     const double2 x = psi[row_i | toff], y = psi[row_j | toff];
                     re = fma(x.x, y.x, fma(x.y, y.y, re));

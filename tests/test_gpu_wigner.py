@@ -232,3 +232,19 @@ def test_config5_slab(engine):
     cols = np.arange(0, 4096, 64)
     ref = c_oracle.wigner_clenshaw(rho, wl["xvec"][cols], wl["xvec"][rows], long_double=True)
     assert rel_err(W[:, cols], ref) < TOL
+
+
+def test_engine_against_thirdparty_golden(engine):
+    """CUDA path against goldens produced by qutip + qiskit themselves (tests/golden/make_golden_thirdparty.py);
+    skips until that file has been generated on a machine that has the two libraries."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "thirdparty_c1_c4.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/thirdparty_c1_c4.npz not generated yet (needs qutip + qiskit)")
+    z = np.load(path)
+    for name in ("c1", "c2", "c3", "c4"):
+        W, rho = engine.state_to_wigner(z[f"{name}_psi"], list(z[f"{name}_traced"]), z[f"{name}_xvec"], return_rho=True)
+        assert np.abs(rho - z[f"{name}_rho"]).max() / np.abs(z[f"{name}_rho"]).max() < 1e-10
+        ref = z[f"{name}_W_clenshaw"]
+        assert np.abs(np.asarray(W) - ref).max() / np.abs(ref).max() < 1e-10

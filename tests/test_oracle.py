@@ -208,3 +208,23 @@ def test_rdbu_lookup_table_of_the_library_equals_the_restated_matplotlib_one():
     assert np.array_equal(img[0, 0], lut[int(0.5 / 99 * 256)]) and np.array_equal(img[1, 1], lut[int(98.5 / 99 * 256)])
     assert img[0, 0][0] > 3 * img[0, 0][2] and img[1, 1][2] > 3 * img[1, 1][0] and img[0, 1][:3].min() > 240
     assert (frame_rgba(np.zeros((3, 3))) == frame_rgba(np.zeros((3, 3)))[0, 0]).all()  # abs_max == 0 -> 5: mid band
+
+
+def test_thirdparty_golden():
+    """Reference-held goldens written by tests/golden/make_golden_thirdparty.py on a machine with qutip + qiskit
+    (absent from this image: the test skips until the file is committed)."""
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "thirdparty_c1_c4.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/thirdparty_c1_c4.npz not generated yet (needs qutip + qiskit: make_golden_thirdparty.py)")
+    from oracle import partial_trace_sv, wigner
+
+    z = np.load(path)
+    for name in ("c1", "c2", "c3", "c4"):
+        rho = partial_trace_sv(z[f"{name}_psi"], list(z[f"{name}_traced"]))
+        assert np.abs(rho - z[f"{name}_rho"]).max() / np.abs(z[f"{name}_rho"]).max() < 1e-10
+        for method in ("clenshaw", "iterative"):
+            W = wigner(z[f"{name}_rho"], z[f"{name}_xvec"], method=method)
+            ref = z[f"{name}_W_{method}"]
+            assert np.abs(W - ref).max() / np.abs(ref).max() < 1e-10
