@@ -52,6 +52,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
                  : "d"(a), "d"(b));
 }
 
+// MT x MT DMMA tiles per warp (an 8 MT x 8 MT block of rho): every gathered element feeds MT MMAs instead of one, so a
+// large trace (D >= 256) is bound by the FP64 tensor pipe rather than by L1 / L2 bandwidth (MT = 1: 2 flops per byte
+// gathered, one warp per 8 x 8 tile -- what the small traces of the named configurations use for parallelism; MT = 4:
+// 8 flops per byte, 64 accumulators per lane).
+template <int MT>
 __global__ void __launch_bounds__(32 * kTraceWarps) trace_sv_dmma_kernel(const TraceSvParams p)
 {
     __shared__ TraceMap map;
@@ -72,10 +77,16 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_sv_dmma_kernel(const T
     const int I = tile / p.tiles, J = tile - I * p.tiles;
     const int gi = lane >> 2, kk = lane & 3;
     const int64_t D = (int64_t)1 << p.n_keep, T = (int64_t)1 << p.n_trace;
-    const int64_t i = (int64_t)I * 8 + gi, j = (int64_t)J * 8 + gi;
-    const bool vi = i < D, vj = j < D;
-    const uint64_t row_i = deposit_bits((uint64_t)(vi ? i : 0), map.keep, p.n_keep);
-    const uint64_t row_j = deposit_bits((uint64_t)(vj ? j : 0), map.keep, p.n_keep);
+    uint64_t row_i[MT], row_j[MT];
+    bool vi[MT], vj[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int64_t i = ((int64_t)I * MT + m) * 8 + gi, j = ((int64_t)J * MT + m) * 8 + gi;
+        vi[m] = i < D;
+        vj[m] = j < D;
+        row_i[m] = deposit_bits((uint64_t)(vi[m] ? i : 0), map.keep, p.n_keep);
+        row_j[m] = deposit_bits((uint64_t)(vj[m] ? j : 0), map.keep, p.n_keep);
+    }
     const double2 *psi = p.psi + (int64_t)b * p.psi_stride;
 
     const int64_t t_begin = (int64_t)split * p.t_per_split;
@@ -86,23 +97,41 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_sv_dmma_kernel(const T
     const uint64_t step4 = deposit_bits(4ull, map.trace, p.n_trace);
     uint64_t toff = deposit_bits((uint64_t)(t_begin + kk), map.trace, p.n_trace);
 
-    double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+    double re0[MT][MT], re1[MT][MT], im0[MT][MT], im1[MT][MT];
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int c = 0; c < MT; ++c) re0[a][c] = re1[a][c] = im0[a][c] = im1[a][c] = 0.0;
     for (int64_t t0 = t_begin; t0 < t_end; t0 += 4) {
         const bool vt = t0 + kk < t_end;
-        double2 x = make_double2(0.0, 0.0), y = make_double2(0.0, 0.0);
-        if (vi && vt) x = psi[row_i | toff];
-        if (vj && vt) y = psi[row_j | toff];
-        dmma_m8n8k4(re0, re1, x.x, y.x);
-        dmma_m8n8k4(re0, re1, x.y, y.y);
-        dmma_m8n8k4(im0, im1, x.y, y.x);
-        dmma_m8n8k4(im0, im1, -x.x, y.y);
+        double2 x[MT], y[MT];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            x[m] = (vi[m] && vt) ? psi[row_i[m] | toff] : make_double2(0.0, 0.0);
+            y[m] = (vj[m] && vt) ? psi[row_j[m] | toff] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int a = 0; a < MT; ++a)
+#pragma unroll
+            for (int c = 0; c < MT; ++c) {
+                dmma_m8n8k4(re0[a][c], re1[a][c], x[a].x, y[c].x);
+                dmma_m8n8k4(re0[a][c], re1[a][c], x[a].y, y[c].y);
+                dmma_m8n8k4(im0[a][c], im1[a][c], x[a].y, y[c].x);
+                dmma_m8n8k4(im0[a][c], im1[a][c], -x[a].x, y[c].y);
+            }
         toff = ((toff | ~mask) + step4) & mask;
     }
     // accumulator fragment: row lane/4, columns (lane%4)*2 + {0, 1}
     double2 *dst = p.out + (((int64_t)split * p.n_sets + set) * p.batch + b) * D * D;
-    const int64_t col = (int64_t)J * 8 + kk * 2;
-    if (vi && col < D) dst[i * D + col] = make_double2(re0, im0);
-    if (vi && col + 1 < D) dst[i * D + col + 1] = make_double2(re1, im1);
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int c = 0; c < MT; ++c) {
+            const int64_t i = ((int64_t)I * MT + a) * 8 + gi;
+            const int64_t col = ((int64_t)J * MT + c) * 8 + kk * 2;
+            if (vi[a] && col < D) dst[i * D + col] = make_double2(re0[a][c], im0[a][c]);
+            if (vi[a] && col + 1 < D) dst[i * D + col + 1] = make_double2(re1[a][c], im1[a][c]);
+        }
 }
 
 __global__ void reduce_splits_kernel(const double2 *__restrict__ partial, double2 *__restrict__ out, int64_t count,
@@ -146,15 +175,18 @@ __global__ void reduce_shots_kernel(const double2 *__restrict__ partial, double2
 
 namespace {
 struct TracePlan {
-    int tiles, splits;
+    int tiles, splits, mt;  // tiles per side of rho, each 8 mt x 8 mt (one warp)
     int64_t t_per_split;
 };
 
-TracePlan plan_trace(int n_keep, int n_trace, int batch, int n_sets, int sm_count)
+TracePlan plan_trace(int n_keep, int n_trace, int batch, int n_sets, int sm_count, int force_mt = 0)
 {
     TracePlan pl;
     const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_trace;
-    pl.tiles = (int)((D + 7) / 8);
+    // register-blocked warps once the plain tiling alone (one warp per 8 x 8 tile) fills the GPU 16 times over
+    pl.mt = ((D + 31) / 32) * ((D + 31) / 32) * batch * n_sets >= 2LL * 16 * sm_count ? 4 : 1;
+    if (force_mt) pl.mt = force_mt;
+    pl.tiles = (int)((D + 8 * pl.mt - 1) / (8 * pl.mt));
     const int64_t base = (int64_t)pl.tiles * pl.tiles * batch * n_sets;  // warps without splitting
     const int64_t want = 16LL * sm_count;                                // 16 warps per SM in flight
     int64_t splits = base < want ? (want + base - 1) / base : 1;
@@ -171,9 +203,10 @@ TracePlan plan_trace(int n_keep, int n_trace, int batch, int n_sets, int sm_coun
 size_t trace_sv_scratch_bytes(int n_keep, int n_trace, int batch, int n_sets)
 {
     // worst case over devices: plan with a generous SM count so the scratch never under-sizes
-    const TracePlan pl = plan_trace(n_keep, n_trace, batch, n_sets, 256);
+    const int splits = std::max(plan_trace(n_keep, n_trace, batch, n_sets, 256, 1).splits,
+                                plan_trace(n_keep, n_trace, batch, n_sets, 256, 4).splits);
     const int64_t D = (int64_t)1 << n_keep;
-    return (size_t)pl.splits * n_sets * batch * D * D * sizeof(double2);
+    return (size_t)splits * n_sets * batch * D * D * sizeof(double2);
 }
 
 cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, const TraceMap *d_maps, int n_sets,
@@ -199,7 +232,8 @@ cudaError_t launch_trace_sv(const double2 *psi, int64_t psi_stride, int batch, c
     const int64_t xdim = (warps + kTraceWarps - 1) / kTraceWarps;
     if (ydim > 65535 || xdim > 0x7fffffffLL) return cudaErrorInvalidValue;
     dim3 grid((unsigned)xdim, (unsigned)ydim);
-    trace_sv_dmma_kernel<<<grid, 32 * kTraceWarps, 0, st>>>(p);
+    if (pl.mt == 4) trace_sv_dmma_kernel<4><<<grid, 32 * kTraceWarps, 0, st>>>(p);
+    else trace_sv_dmma_kernel<1><<<grid, 32 * kTraceWarps, 0, st>>>(p);
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -235,7 +269,8 @@ cudaError_t launch_trace_sv_accumulate(const double2 *psi, int64_t psi_stride, i
     const int64_t warps = (int64_t)pl.tiles * pl.tiles * pl.splits;
     const int64_t xdim = (warps + kTraceWarps - 1) / kTraceWarps;
     if (ydim > 65535 || xdim > 0x7fffffffLL) return cudaErrorInvalidValue;
-    trace_sv_dmma_kernel<<<dim3((unsigned)xdim, (unsigned)ydim), 32 * kTraceWarps, 0, st>>>(p);
+    if (pl.mt == 4) trace_sv_dmma_kernel<4><<<dim3((unsigned)xdim, (unsigned)ydim), 32 * kTraceWarps, 0, st>>>(p);
+    else trace_sv_dmma_kernel<1><<<dim3((unsigned)xdim, (unsigned)ydim), 32 * kTraceWarps, 0, st>>>(p);
     if (launches) ++*launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -795,13 +795,22 @@ __device__ __forceinline__ void sym_unit(int64_t t, int U, int &a, int &b)
     b = r + (int)(t - ((int64_t)r * U - (int64_t)r * (r - 1) / 2));
 }
 
+// Unit (within the launch's range) of slot c of the thread that owns `chunk` = tile * blockDim + tid: the tile's units are
+// dealt out so that the threads of a warp hold CONSECUTIVE units for a given c -- a store instruction then writes 32
+// consecutive doubles of a grid row (the four points W[a or S-1-a][b or S-1-b]; the transposed four stay strided by rows).
+__device__ __forceinline__ int64_t sym_idx(int64_t chunk, int c, int cl)
+{
+    const int tid = threadIdx.x;
+    return (chunk - tid) * cl + (int64_t)c * blockDim.x + tid;
+}
+
 template <int CL>
 __device__ __forceinline__ void sym_load(const WigParams &p, int64_t chunk, SymPoints<CL> &s, int (&ua)[CL], int (&ub)[CL],
                                          const double2 h)
 {
 #pragma unroll
     for (int c = 0; c < CL; ++c) {
-        const int64_t t = p.sym_first + min(chunk * CL + c, p.sym_units - 1);
+        const int64_t t = p.sym_first + min(sym_idx(chunk, c, CL), p.sym_units - 1);
         sym_unit(t, p.sym_U, ua[c], ub[c]);
         s.al[c] = p.g * __ldg(p.xvec + ua[c]);
         s.be[c] = p.g * __ldg(p.xvec + ub[c]);
@@ -822,7 +831,7 @@ __device__ __forceinline__ void sym_store(const WigParams &p, int frame, int64_t
     const int S = p.nx;
 #pragma unroll
     for (int c = 0; c < CL; ++c) {
-        if (chunk * CL + c >= p.sym_units) continue;
+        if (sym_idx(chunk, c, CL) >= p.sym_units) continue;
         const double e = exp(-0.5 * s.B[c]) * p.scale;
         const int a = ua[c], b = ub[c], am = S - 1 - a, bm = S - 1 - b;
 #pragma unroll
@@ -1055,7 +1064,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : TRI
                 const double2 h = cb[0];
 #pragma unroll
                 for (int c = 0; c < CL; ++c) {
-                    const int64_t t = p.sym_first + min(chunk * CL + c, p.sym_units - 1);
+                    const int64_t t = p.sym_first + min(sym_idx(chunk, c, CL), p.sym_units - 1);
                     sym_unit(t, p.sym_U, ua[c], ub[c]);
                     s.al[c] = p.g * __ldg(p.xvec + ua[c]);
                     s.be[c] = p.g * __ldg(p.xvec + ub[c]);
@@ -1091,7 +1100,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : TRI
         const int S = p.nx;
 #pragma unroll
         for (int c = 0; c < CL; ++c) {
-            if (chunk * CL + c >= p.sym_units) continue;
+            if (sym_idx(chunk, c, CL) >= p.sym_units) continue;
             const double e = exp(-0.5 * s.B[c]) * p.scale;
             const int a = ua[c], b = ub[c], am = S - 1 - a, bm = S - 1 - b;
 #pragma unroll
