@@ -35,7 +35,7 @@ MAX_REGS_FOR = [("wigner_stream_kernelILi4ELi256", 168), ("wigner_stream_kernelI
                 ("wigner_sym_resident_kernelILi2ELi128", 248), ("wigner_sym_resident_kernelILi2ELi192", 168),
                 ("wigner_sym_diag_kernelILi2ELi256", 248), ("wigner_sym_diag_kernelILi2ELi384", 168),
                 ("wigner_sym_diag_kernelILi1ELi256", 248),
-                ("wigner_sym_resident_kernelILi4ELi256", 255), ("wigner_sym_diag_kernelILi4ELi256", 255),
+                ("wigner_sym_resident_kernelILi4ELi256", 255), ("wigner_sym_resident_mixed_kernelILi4ELi3ELi256", 255), ("wigner_sym_diag_kernelILi4ELi256", 255),
                 ("wigner_sym_diag_parked_kernelILi4ELi256", 248), ("wigner_sym_diag_parked_kernelILi3ELi384", 168)]
 
 

@@ -804,13 +804,15 @@ __device__ __forceinline__ int64_t sym_idx(int64_t chunk, int c, int cl)
     return (chunk - tid) * cl + (int64_t)c * blockDim.x + tid;
 }
 
+// A thread's CL units are first, first + stride, ... (within the launch's range); sym_idx() above is the case
+// first = tile base + tid, stride = blockDim.
 template <int CL>
-__device__ __forceinline__ void sym_load(const WigParams &p, int64_t chunk, SymPoints<CL> &s, int (&ua)[CL], int (&ub)[CL],
-                                         const double2 h)
+__device__ __forceinline__ void sym_load(const WigParams &p, int64_t first, int stride, SymPoints<CL> &s, int (&ua)[CL],
+                                         int (&ub)[CL], const double2 h)
 {
 #pragma unroll
     for (int c = 0; c < CL; ++c) {
-        const int64_t t = p.sym_first + min(sym_idx(chunk, c, CL), p.sym_units - 1);
+        const int64_t t = p.sym_first + min(first + (int64_t)c * stride, p.sym_units - 1);
         sym_unit(t, p.sym_U, ua[c], ub[c]);
         s.al[c] = p.g * __ldg(p.xvec + ua[c]);
         s.be[c] = p.g * __ldg(p.xvec + ub[c]);
@@ -824,14 +826,14 @@ __device__ __forceinline__ void sym_load(const WigParams &p, int64_t chunk, SymP
 }
 
 template <int CL>
-__device__ __forceinline__ void sym_store(const WigParams &p, int frame, int64_t chunk, const SymPoints<CL> &s,
+__device__ __forceinline__ void sym_store(const WigParams &p, int frame, int64_t first, int stride, const SymPoints<CL> &s,
                                           const int (&ua)[CL], const int (&ub)[CL])
 {
     double *Wf = p.W + (int64_t)frame * p.w_stride;
     const int S = p.nx;
 #pragma unroll
     for (int c = 0; c < CL; ++c) {
-        if (sym_idx(chunk, c, CL) >= p.sym_units) continue;
+        if (first + (int64_t)c * stride >= p.sym_units) continue;
         const double e = exp(-0.5 * s.B[c]) * p.scale;
         const int a = ua[c], b = ub[c], am = S - 1 - a, bm = S - 1 - b;
 #pragma unroll
@@ -884,14 +886,78 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_sym_resident_kernel(cons
         SymPoints<CL> s;
         int ua[CL], ub[CL];
         const int64_t chunk = (int64_t)tif * THREADS + tid;
-        sym_load<CL>(p, chunk, s, ua, ub, cs_s[0]);
+        sym_load<CL>(p, sym_idx(chunk, 0, CL), THREADS, s, ua, ub, cs_s[0]);
         int pos = 1;
-        const int lead = sym_lead(p, THREADS);
-        for (int K = 2; K <= N; ++K) {
-            sym_diagonal<CL>(s, cs_s + pos, tab_s + pos, K, lead);
+        for (int K = 2; K <= N; ++K) {  // (no staggered warps here: with ~8 trips per diagonal the single steps cost more)
+            sym_diagonal<CL>(s, cs_s + pos, tab_s + pos, K);
             pos += K + 1;
         }
-        sym_store<CL>(p, frame, chunk, s, ua, ub);
+        sym_store<CL>(p, frame, sym_idx(chunk, 0, CL), THREADS, s, ua, ub);
+    }
+    leave_grid(p);
+}
+
+// MIXED tile for the resident cutoffs: the first half of the CTA's warps take CLA units per thread, the second half CLB.
+// Warps w and w + 4 share a scheduler, so with 8 warps every scheduler holds one warp of each kind and CLA + CLB units
+// per lane.  Why: a 1024 x 1024 grid (and 4 frames of 512 x 512) is 131 328 units = 887 per SM; the 4-unit tile covers
+// that in one round of 129 CTAs of 1024 units (19 SMs idle, every busy scheduler 8 units per lane), the <4, 3> tile in
+// one round of 147 CTAs of 896 units -- 7 units per lane, every SM busy.
+template <int CL>
+__device__ __forceinline__ void sym_resident_tile(const WigParams &p, const double2 *cs_s, const double4 *tab_s, int frame,
+                                                  int64_t first, int stride)
+{
+    SymPoints<CL> s;
+    int ua[CL], ub[CL];
+    sym_load<CL>(p, first, stride, s, ua, ub, cs_s[0]);
+    int pos = 1;
+    for (int K = 2; K <= p.N; ++K) {
+        sym_diagonal<CL>(s, cs_s + pos, tab_s + pos, K);
+        pos += K + 1;
+    }
+    sym_store<CL>(p, frame, first, stride, s, ua, ub);
+}
+
+template <int CLA, int CLB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) wigner_sym_resident_mixed_kernel(const WigParams p)
+{
+    constexpr int HALF = THREADS / 2, TILE = HALF * (CLA + CLB);
+    extern __shared__ __align__(128) unsigned char smem[];
+    double4 *tab_s = reinterpret_cast<double4 *>(smem);
+    double2 *cs_s = reinterpret_cast<double2 *>(smem + (size_t)p.R_tot * 32);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)p.R_tot * 48);
+    int *slot = reinterpret_cast<int *>(bar + 1);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    uint32_t phase = 0;
+    int loaded_frame = -1;
+    TileCursor tc{0, 0};
+    if (p.pro_mode) fused_prologue(p);
+
+    for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
+        const int frame = tile / p.tiles_per_frame;
+        const int tif = tile - frame * p.tiles_per_frame;
+        if (frame != loaded_frame) {
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
+                const bool first = loaded_frame < 0;
+                mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
+                if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
+                bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            loaded_frame = frame;
+        }
+        const int64_t base = (int64_t)tif * TILE;
+        if (tid < HALF) sym_resident_tile<CLA>(p, cs_s, tab_s, frame, base + tid, HALF);
+        else sym_resident_tile<CLB>(p, cs_s, tab_s, frame, base + HALF * CLA + (tid - HALF), HALF);
     }
     leave_grid(p);
 }
@@ -959,7 +1025,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
             const double4 *tb = tab_s + (size_t)st * cap;
             int pos = 0;
             if (!loaded) {
-                sym_load<CL>(p, chunk, s, ua, ub, cb[0]);
+                sym_load<CL>(p, sym_idx(chunk, 0, CL), THREADS, s, ua, ub, cb[0]);
                 loaded = true;
                 pos = 1;
             }
@@ -972,7 +1038,7 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
             if ((tid & 31) == 0) mbar_arrive(&empty[st]);
             if (tid == 0 && pK <= N) produce();
         }
-        sym_store<CL>(p, frame, chunk, s, ua, ub);
+        sym_store<CL>(p, frame, sym_idx(chunk, 0, CL), THREADS, s, ua, ub);
     }
     leave_grid(p);
 }
@@ -1251,7 +1317,7 @@ cudaError_t launch_pack_rho(const double2 *rho, int64_t ld, int64_t rho_stride, 
 namespace {
 
 constexpr int kStages = 4, kChunk = 256;
-constexpr int kVariants = 22;
+constexpr int kVariants = 23;
 constexpr int kDiagStages = 3;
 
 const char *const kKernelNames[kVariants] = {
@@ -1277,6 +1343,7 @@ const char *const kKernelNames[kVariants] = {
     "_ZN2bq29wigner_sym_diag_parked_kernelILi4ELi256ELi2ELi4EEEvNS_9WigParamsE",
     "_ZN2bq29wigner_sym_diag_parked_kernelILi3ELi384ELi2ELi4EEEvNS_9WigParamsE",
     "_ZN2bq29wigner_sym_diag_parked_kernelILi4ELi256ELi2ELi8EEEvNS_9WigParamsE",
+    "_ZN2bq32wigner_sym_resident_mixed_kernelILi4ELi3ELi256EEEvNS_9WigParamsE",
 };
 
 struct Patched {
@@ -1377,6 +1444,7 @@ struct VariantInfo {
     const void *plain;
     int kind;  // 0 resident, 1 stream, 2 diag ring, 3 sym resident, 4 sym ring, 5 sym ring with parked accumulators
     int pts, threads, stages;
+    int tile_units = 0;  // units per tile when that is not pts * threads (the mixed tile)
 };
 const VariantInfo kVariantInfo[kVariants] = {
     {(const void *)wigner_resident_kernel<4, 256, 2>, 0, 4, 256, 0},
@@ -1401,6 +1469,7 @@ const VariantInfo kVariantInfo[kVariants] = {
     {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 4>, 5, 4, 256, 2},
     {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2, 4>, 5, 3, 384, 2},
     {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 8>, 5, 4, 256, 2},
+    {(const void *)wigner_sym_resident_mixed_kernel<4, 3, 256>, 3, 4, 256, 0, 896},
 };
 
 size_t variant_smem(const VariantInfo &v, int N, int R_tot)
@@ -1537,7 +1606,8 @@ cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *che
                 dev.sass_mode = pass;  // 0: nvcc's schedule, 1: the patched image
                 VCHK(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned int) * 4, st));
                 VCHK(cudaMemsetAsync(d_W, 0xFF, sizeof(double) * Wa.size(), st));
-                const int64_t sym_chunks = p.sym ? (p.sym_units + vi.pts - 1) / vi.pts : -1;
+                int64_t sym_chunks = p.sym ? (p.sym_units + vi.pts - 1) / vi.pts : -1;
+                if (vi.tile_units) sym_chunks = (p.sym_units + vi.tile_units - 1) / vi.tile_units * vi.threads;
                 cudaError_t e = run(vi.plain, v, vi.threads, smem, p, vi.pts, dev, st, nullptr, sym_chunks);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(pass ? Wb.data() : Wa.data(), d_W, sizeof(double) * Wa.size(), cudaMemcpyDeviceToHost, st);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1594,6 +1664,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             int variant, cl, threads;
             double eff;
             int stages = kDiagStages, parked = 0;  // ring kernels: stages of the ring; Horner accumulators in shared memory
+            int tile_units = 0;                     // units per tile when that is not cl * threads (the mixed tile)
         };
         static const SymVariant resident_variants[] = {
             {(const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 3, 128, 1.00},
@@ -1602,6 +1673,9 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_resident_kernel<1, 256, 2>, 13, 1, 256, 0.80},
             {(const void *)wigner_sym_resident_kernel<1, 128, 4>, 9, 1, 128, 0.75},
             {(const void *)wigner_sym_resident_kernel<4, 256, 1>, 17, 4, 256, 0.92},  // one CTA per SM: 1024 units per round
+            // 4 + 3 units per pair of warps: 896 units per CTA at the cost of a 3.5-unit tile (cl below is what the
+            // launcher's tile arithmetic uses for the larger half; the cost model takes tile_units)
+            {(const void *)wigner_sym_resident_mixed_kernel<4, 3, 256>, 22, 4, 256, 0.92, kDiagStages, 0, 896},
         };
         static const SymVariant ring_variants[] = {
             {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
@@ -1621,7 +1695,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             return v.parked ? ((ring + 15) & ~(size_t)15) + (size_t)v.cl * 8 * v.threads * sizeof(double2) : ring;
         };
         const SymVariant *vars = resident ? resident_variants : ring_variants;
-        const int nvars = resident ? 6 : 8;
+        const int nvars = resident ? 7 : 8;
         struct Cand {
             const SymVariant *v;
             size_t smem;
@@ -1653,8 +1727,9 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 c.smem = smem;
                 c.occ = occ;
                 c.ctas = (int64_t)occ * dev.sm_count;
-                c.tiles = (((p.sym_units + v.cl - 1) / v.cl + v.threads - 1) / v.threads) * p.batch;
-                c.round_cost = (double)v.cl * v.threads * occ / eff;
+                const int64_t tile_units = v.tile_units ? v.tile_units : (int64_t)v.cl * v.threads;
+                c.tiles = ((p.sym_units + tile_units - 1) / tile_units) * p.batch;
+                c.round_cost = (double)tile_units * occ / eff;
             }
         }
         bool pro_done = false;  // the fused prologue builds the coefficient stream once: in the first launch of the call
@@ -1666,7 +1741,8 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             q.sym_delay = dev.sym_delay;
             if (pro_done) q.pro_mode = 0;
             pro_done = true;
-            return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, (count + v.cl - 1) / v.cl);
+            const int64_t chunks = v.tile_units ? (count + v.tile_units - 1) / v.tile_units * v.threads : (count + v.cl - 1) / v.cl;
+            return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, chunks);
         };
         // A last round that fills only part of the machine still costs a whole tile.  Tried and measured (tools/
         // sym_split_sweep.py, profiles/r1d_sym_split.txt): whole rounds in one launch and the remainder in a SECOND

@@ -133,6 +133,7 @@ class Engine:
         15: "wigner_sym_diag_kernel<2,384,3>", 16: "wigner_sym_diag_kernel<1,256,3>", 17: "wigner_sym_resident_kernel<4,256,1>",
         18: "wigner_sym_diag_kernel<4,256,3>", 19: "wigner_sym_diag_parked_kernel<4,256,2>",
         20: "wigner_sym_diag_parked_kernel<3,384,2>", 21: "wigner_sym_diag_parked_kernel<4,256,2,trip8>",
+        22: "wigner_sym_resident_mixed_kernel<4,3,256>",
     }
 
     def last_wigner_kernel(self) -> str:

@@ -183,7 +183,7 @@ def test_grid_verdict_follows_the_tensor_not_its_address(engine):
     assert len(seen) < len(grids)  # the allocator did recycle an address (otherwise this test shows nothing)
 
 
-RESIDENT_VARIANTS = [8, 9, 11, 12, 13, 17]
+RESIDENT_VARIANTS = [8, 9, 11, 12, 13, 17, 22]
 RING_VARIANTS = [10, 14, 15, 16, 18, 19, 20, 21]
 
 
