@@ -296,14 +296,96 @@ class Giveup(Exception):
 
 
 # ------------------------------------------------------------------------------------------------
+# the Clenshaw step's own structure (an order the greedy search does not find)
+# ------------------------------------------------------------------------------------------------
+def clenshaw_ranks(body, dslots, reads, dfma_index, last_writer):
+    """Rank of every DFMA of a loop made of Clenshaw steps, or None when the loop is not of that shape.
+
+    A step of unit u is  tn = B_u tz + ty;  y0r' = tx y1r + cx;  y0i' = tx y1i + cy;  y1r' = tn y1r + y0r;  y1i' = tn y1i + y0i
+    (B_u loop-invariant, tz ty tx cx cy loaded per step).  The order   [tn of every unit]  then per unit
+    y0r' -> y1r' -> y1i' -> y0i'   shares an operand in the same slot between every two neighbours (tz ty along the tn's;
+    y1r, tn, y1i inside a unit's chain; tx from one unit's y0i' to the next unit's y0r'): 2 register-file cycles per DFMA except
+    at the two seams of a step (into and out of the tn block) -- 42 per step of four units against ~44 for the greedy search."""
+    nd = len(dslots)
+    n_lds = [0] * nd
+    inv = [None] * nd       # loop-invariant register operand (never written in the body, not loaded)
+    dsrc = [[] for _ in range(nd)]
+    lsrc = [[] for _ in range(nd)]
+    for j, k in enumerate(dslots):
+        for slot, r, p in reads[k]:
+            if p is None:
+                if r not in last_writer:
+                    inv[j] = r
+            elif body[p].kind == "lds":
+                n_lds[j] += 1
+                lsrc[j].append((p, r - body[p].dst_base))
+            else:
+                dsrc[j].append(dfma_index[p])
+    is_tn = [n_lds[j] == 2 and inv[j] is not None and not dsrc[j] for j in range(nd)]
+    is_n0 = [n_lds[j] == 2 and not is_tn[j] for j in range(nd)]
+    is_n1 = [n_lds[j] == 0 and any(is_tn[i] for i in dsrc[j]) for j in range(nd)]
+    if sum(is_tn) * 5 != nd or sum(is_n0) != 2 * sum(is_tn) or sum(is_n1) != 2 * sum(is_tn):
+        return None
+    units = sorted({inv[j] for j in range(nd) if is_tn[j]})
+    # steps: the tn's in body order, one per unit and step
+    step_of, unit_of = [None] * nd, [None] * nd
+    seen = {}
+    for j in range(nd):
+        if is_tn[j]:
+            u = units.index(inv[j])
+            step_of[j], unit_of[j] = seen.get(u, 0), u
+            seen[u] = step_of[j] + 1
+    n_steps = max(seen.values())
+    if any(v != n_steps for v in seen.values()):
+        return None
+    comp = [None] * nd  # 0 real part, 1 imaginary part
+    for j in range(nd):
+        if is_n1[j]:
+            t = next(i for i in dsrc[j] if is_tn[i])
+            step_of[j], unit_of[j] = step_of[t], unit_of[t]
+    # y0' = tx y1 + c reads the y1 its unit's y1' of the same step reads: match them through that operand
+    y1_of = {}  # (operand register, its producer) -> the y1' that reads it as y1 or y0 (a y0' only ever reads the y1)
+    for j, k in enumerate(dslots):
+        if is_n1[j]:
+            for slot, r, p in reads[k]:
+                if not (p is not None and body[p].kind == "dfma" and is_tn[dfma_index[p]]):
+                    y1_of[(r, p)] = j
+    for j, k in enumerate(dslots):
+        if is_n0[j]:
+            m = next((y1_of.get((r, p)) for slot, r, p in reads[k] if (r, p) in y1_of), None)
+            if m is None:
+                return None
+            step_of[j], unit_of[j] = step_of[m], unit_of[m]
+            comp[j] = comp[m] = None  # paired below
+    # pair every y0' with the y1' that shares its y1; the pair whose c comes from the lower half of its load is the real part
+    for j, k in enumerate(dslots):
+        if is_n0[j]:
+            m = next(y1_of[(r, p)] for slot, r, p in reads[k] if (r, p) in y1_of)
+            c_off = max(off for p_, off in lsrc[j])  # (tx: offset 0 of the tab load; cx / cy: offsets 0 / 2 of the cs load)
+            comp[j] = comp[m] = 0 if c_off == 0 else 1
+    if any(step_of[j] is None or unit_of[j] is None for j in range(nd)):
+        return None
+    ranks = [0] * nd
+    for j in range(nd):
+        if is_tn[j]:
+            ranks[j] = (step_of[j], 0, unit_of[j], 0)
+        else:
+            chain = {(0, 0): 0, (1, 0): 1, (1, 1): 2, (0, 1): 3}[(0 if is_n0[j] else 1, comp[j] or 0)]  # y0r' y1r' y1i' y0i'
+            ranks[j] = (step_of[j], 1, unit_of[j], chain)
+    return ranks
+
+
+# ------------------------------------------------------------------------------------------------
 # the re-scheduler
 # ------------------------------------------------------------------------------------------------
-def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=None, jitter=8):
+def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=None, jitter=8, pattern=False):
     """body: the instructions of one loop iteration, the last one being the backward branch;
     live_after: registers read after the loop exit before being rewritten;
     extra_regs: registers no instruction of the kernel uses (free for the loop's temporaries);
     rng: None = the deterministic greedy order; a random.Random = the same greedy pass with its ties (and
     near-ties) broken at random -- patch_file keeps the best of several such passes by the issue model.
+    pattern: order the DFMAs by the Clenshaw step's own structure (clenshaw_ranks below) wherever the dependences allow,
+    instead of by the greedy one-step look-ahead.
     Returns (new 128-bit words, info) or raises Giveup."""
     n = len(body)
     for x in body:
@@ -427,6 +509,10 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
         for slot, r, p in reads[k]:
             if p is None and final_writer.get(r) is not None and body[final_writer[r]].kind == "dfma":
                 carried.append((dfma_index[final_writer[r]], j))
+
+    rank = clenshaw_ranks(body, dslots, reads, dfma_index, last_writer) if pattern else None
+    if pattern and rank is None:
+        raise Giveup("not a Clenshaw step loop the pattern order understands")
 
     def previous_contents(k, r):
         """values that occupy register r before pinned instruction k defines it (live-in or earlier pinned)"""
@@ -552,7 +638,7 @@ def reschedule(body, verbose=False, live_after=frozenset(), extra_regs=(), rng=N
                     return (c1 + c2, c1, deadline[j] - pos + rng.randint(0, jitter), rng.random())
                 return (c1 + c2, c1, deadline[j] - pos, dslots[j])
 
-            j = min(pick_from, key=score)
+            j = min(pick_from, key=(lambda i: (rank[i], dslots[i])) if rank is not None else score)
         waited = [pending.index(p) for p in lpreds[j] if p in pending]
         if waited:
             # This DFMA has to wait on the scoreboard anyway (which costs it its reuse-cache operands): let it also
@@ -827,6 +913,11 @@ def patch_file(src, dst, min_dfma=24, verbose=False, max_regs=None, only=None, m
                 extra = tuple(range(first + first % 2, limit - 2))
             live_after = live_registers_at(ins, hi + 1)
             best, why = None, None
+            try:  # the structured order first (Clenshaw-step loops of >= 3 units per thread)
+                cand = reschedule(body, False, live_after=live_after, extra_regs=extra, pattern=True)
+                best = ((cand[1]["after"], cand[1]["bumped"], cand[1]["used_max"]), cand)
+            except Giveup:
+                pass
             for t in range(max(1, trials)):
                 # trial 0 is the deterministic pass; the others break the greedy pass's ties at random (fixed seeds:
                 # the build is reproducible).  The best schedule by (model cycles, extra stall, registers) is kept.
