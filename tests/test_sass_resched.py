@@ -236,3 +236,56 @@ def test_read_barrier_regression_on_a_doctored_loop(images):
             if x.kind == "lds":
                 assert (words[k] >> 110) & 7 != 4, "a load's write barrier landed on the read barrier's index"
     assert done >= 1
+
+
+def test_every_loaded_operand_is_waited_for(images):
+    """Scoreboard audit of every patched loop: a DFMA that reads a register an LDS of the body wrote must be preceded --
+    between that load and itself, in issue order, the back edge included -- by an instruction that waits on the write barrier
+    of that load or of a YOUNGER load (shared-memory loads complete in issue order, which ptxas's own code relies on), and
+    the load must carry a write barrier at all unless a younger one does.  A missing wait is a timing-dependent wrong
+    result that the bit-identity checks on an idle GPU may never see."""
+    orig, patched = images
+    audited = 0
+    for name, ip in patched.items():
+        io = orig[name]
+        loops = sr.find_loops(io)
+        for lo, hi in loops:
+            body = ip[lo:hi + 1]
+            if all(x.word == y.word for x, y in zip(io[lo:hi + 1], body)):
+                continue
+            if any(lo <= l2 and h2 <= hi and (l2, h2) != (lo, hi) for l2, h2 in loops):
+                continue
+            for x in body:
+                sr.classify(x)
+            n = len(body)
+            lds = [k for k, x in enumerate(body) if x.kind == "lds"]
+            for k, x in enumerate(body):
+                if x.kind != "dfma":
+                    continue
+                for slot, r in x.src:
+                    # the last writer of r before position k, walking backwards around the loop
+                    for back in range(1, n + 1):
+                        w = body[(k - back) % n]
+                        if r in w.dst or (r + 1) in w.dst:
+                            break
+                    else:
+                        continue  # loop-invariant operand
+                    if w.kind != "lds":
+                        continue
+                    kw = (k - back) % n
+                    # barriers a wait may name: that load's own, or any younger load's issued before the reader
+                    span = [(kw + d) % n for d in range(0, back)]  # kw .. k-1 in issue order
+                    ok_bars = set()
+                    waited = False
+                    for pos in span:
+                        y = body[pos]
+                        if pos != kw and (y.word >> 116) & 0x3F & sum(1 << b for b in ok_bars):
+                            waited = True
+                            break
+                        if y.kind == "lds" and (y.word >> 110) & 7 != 7:
+                            ok_bars.add((y.word >> 110) & 7)
+                    if not waited and (x.word >> 116) & 0x3F & sum(1 << b for b in ok_bars):
+                        waited = True
+                    assert waited, f"{name} {x.addr:#x}: {x.text} reads R{r} of {w.text} with no wait in between"
+                    audited += 1
+    assert audited > 500
