@@ -730,13 +730,24 @@ __device__ __forceinline__ double4 sym_diagonal_steps8(P &s, const double2 *__re
     const double4 *tp = td + 2;
     const int m = K - 2;
     int r = 0;
-    const int nl = min(lead, m);
+    // `lead` (0 or 4: the stagger between the warps of a scheduler) and what the 8-step trips leave over run as trips of FOUR
+    // steps -- re-scheduled loops as well -- so that at most three single steps per diagonal are left (single steps cost
+    // ~4x a step of a trip: 3 % of the cutoff-1024 kernel's time went into 5.5 of them per diagonal)
+    const int nl = min(lead, m) & ~3;
 #pragma unroll 1
-    for (; r < nl; ++r) sym_step<CL>(s, cp[r], tp[r]);
+    for (; r < nl; r += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sym_step<CL>(s, cp[r + u], tp[r + u]);
+    }
 #pragma unroll 1
     for (; r + 7 < m; r += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) sym_step<CL>(s, cp[r + u], tp[r + u]);
+    }
+#pragma unroll 1
+    for (; r + 3 < m; r += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sym_step<CL>(s, cp[r + u], tp[r + u]);
     }
 #pragma unroll 1
     for (; r < m; ++r) sym_step<CL>(s, cp[r], tp[r]);
@@ -1675,7 +1686,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_resident_kernel<4, 256, 1>, 17, 4, 256, 0.92},  // one CTA per SM: 1024 units per round
             // 4 + 3 units per pair of warps: 896 units per CTA at the cost of a 3.5-unit tile (cl below is what the
             // launcher's tile arithmetic uses for the larger half; the cost model takes tile_units)
-            {(const void *)wigner_sym_resident_mixed_kernel<4, 3, 256>, 22, 4, 256, 0.92, kDiagStages, 0, 896},
+            {(const void *)wigner_sym_resident_mixed_kernel<4, 3, 256>, 22, 4, 256, 1.04, kDiagStages, 0, 896},
         };
         static const SymVariant ring_variants[] = {
             {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
@@ -1719,7 +1730,10 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 // (the 2-unit tile loses ~6 % to the 3-unit one at cutoff 64 and wins ~5 % at cutoff <= 32; parked
                 // accumulators cost 16 shared-memory accesses per unit and diagonal: 0.92 of the 3-unit ring tile at
                 // cutoff 128, 0.99 at 256, 1.09 at 1024 -- profiles/r1d_sym_variants_parked.txt)
-                const double eff = (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93
+                // (round-2 sweep, profiles/r2_sym_variants.txt: the 2-unit tile per unit against the 3-unit one 1.07-1.09 at
+                // cutoff <= 32, 0.94 at cutoff 64; the mixed tile 1.02-1.05)
+                const double eff = (resident && v.cl == 2 && v.threads == 128) ? v.eff * (p.N > 32 ? 0.97 : 1.10)
+                                   : (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93
                                    : v.parked           ? v.eff * (1.10 - 23.0 / p.N) * (v.parked == 2 ? (p.N >= 512 ? 1.009 : 0.99) : 1.0)
                                                         : v.eff;
                 Cand &c = cand[ncand++];
@@ -1752,9 +1766,14 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
         const Cand *best = nullptr, *split_main = nullptr, *split_tail = nullptr;
         double best_cost = 0.0;
         int64_t split_tpf = 0;
+        // a grid so small that one 128-thread CTA per SM with ONE unit per thread covers it: a tile's duration is then
+        // latency (~ 46 us + 17.5 us per unit per thread at cutoff 64), not throughput -- the smallest tile wins
+        // (200 x 200 at cutoff 16: 17.8 us against 20.1-21.3 us for the tiles the throughput model prefers)
+        const bool tiny = resident && units <= 128LL * dev.sm_count && dev.sym_force < 0;
         for (int i = 0; i < ncand; ++i) {
             const Cand &c = cand[i];
             if (dev.sym_force >= 0 && c.v->variant != dev.sym_force) continue;
+            if (tiny && !(c.v->cl == 1 && c.v->threads == 128)) continue;
             const double cost = (double)((c.tiles + c.ctas - 1) / c.ctas) * c.round_cost;
             if (!best || cost < best_cost) {
                 best = &c;

@@ -12,9 +12,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [(16, 200, 1), (16, 2048, 1), (32, 400, 64), (32, 2048, 1), (64, 1024, 1), (64, 2048, 1), (128, 2048, 1),
-         (256, 2048, 1), (512, 1024, 1), (1024, 4096, 1)]
-RESIDENT = {"auto": None, "cl4x256": 17, "cl3x128": 8, "cl2x192": 12, "cl2x128": 11, "cl1x256": 13, "cl1x128": 9}
-RING = {"auto": None, "cl4x256p": 19, "cl3x384p": 20, "cl4x256r": 18, "cl3x256": 10, "cl2x384": 15, "cl2x256": 14, "cl1x256": 16}
+         (256, 2048, 1), (512, 1024, 1), (512, 2048, 1), (1024, 4096, 1)]
+RESIDENT = {"auto": None, "mix43x256": 22, "cl4x256": 17, "cl3x128": 8, "cl2x192": 12, "cl2x128": 11, "cl1x256": 13, "cl1x128": 9}
+RING = {"auto": None, "cl4x256p8": 21, "cl4x256p": 19, "cl3x384p": 20, "cl4x256r": 18, "cl3x256": 10, "cl2x384": 15, "cl2x256": 14, "cl1x256": 16}
 
 
 def child():
