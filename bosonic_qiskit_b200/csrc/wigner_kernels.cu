@@ -1094,6 +1094,10 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : TRI
         const int tif = tile - frame * p.tiles_per_frame;
         const double2 *cs_g = p.cs + (int64_t)frame * p.cs_stride;
 
+        // (A CTA that took a RUN of tiles from the counter moves on without the barrier inside next_tile: the refills below
+        // overwrite the ring stages, so every warp must have finished the previous tile's last groups first.  Found with
+        // 3- and 2-unit variants of this kernel, whose 2 700+ tiles of a 4096 x 4096 grid are grabbed in runs of 2-3: NaNs.)
+        __syncthreads();
         // The ring: ALL stages are filled when the tile starts, and a stage is refilled with the next group by
         // whichever warp is the LAST to finish with its contents -- nobody ever waits for a stage to drain, and a
         // group's copy is in flight for as long as the groups in the other stages take to consume.  (Before: one

@@ -210,3 +210,29 @@ def test_every_symmetric_kernel_variant(engine, variant):
     finally:
         engine.set_grid_sharing(True)
         engine.set_sym_variant(None)
+
+
+@pytest.mark.parametrize("variant", [19, 21])
+def test_parked_ring_kernel_with_tiles_taken_in_runs(engine, variant):
+    """Enough one-tile frames that the persistent CTAs take tiles from the counter in RUNS (grab >= 2): a CTA then moves to
+    its next tile without the block-wide barrier of the counter path, and the ring refills at the start of a tile must not
+    overtake warps still reading the previous tile's last groups (they once did: NaNs on a 4096 x 4096 grid)."""
+    N, S, frames = 80, 64, 2500
+    rng = np.random.default_rng(3)
+    base = workloads.random_rho(N, seed=9, rank=3)
+    rho = np.stack([base * (1.0 + 0.001 * k) for k in range(8)])
+    rho = np.concatenate([rho] * (frames // 8 + 1))[:frames]
+    x = np.linspace(-5, 5, S)
+    try:
+        engine.set_sym_variant(variant)
+        W = np.asarray(engine.wigner(rho, x)).copy()
+    finally:
+        engine.set_sym_variant(None)
+    assert np.isfinite(W).all()
+    for k in range(8):
+        ref = wigner_clenshaw(rho[k], x)
+        for f in range(k, frames, 8 * 37):  # the same rho recurs every 8 frames: all copies must agree with the oracle
+            assert np.abs(W[f] - ref).max() / np.abs(ref).max() < 1e-10, (k, f)
+    # ... and every copy of a frame bit for bit with its first occurrence
+    for k in range(8):
+        assert all(np.array_equal(W[f], W[k]) for f in range(k, frames, 8)), k
