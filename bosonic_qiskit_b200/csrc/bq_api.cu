@@ -234,6 +234,7 @@ struct WigSource {
 int wigner_core(bq_handle_t h, const WigSource &src, int N, int batch, const double *d_x, int nx, const double *d_y, int ny,
                 double g, double *d_W, cudaStream_t st, bool mirror_grid)
 {
+    NvtxRange nvtx_range("K3 wigner (coefficient stream + Clenshaw launch)");
     if (batch == 0 || nx == 0 || ny == 0) return BQ_OK;
     const double4 *tab = nullptr;
     int rc = get_tab(h, N, st, &tab);
@@ -374,6 +375,7 @@ int stage_grid(bq_handle_t h, const double *x, int nx, const double *y, int ny, 
 int trace_sv_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced, int n_sets,
                   int batch, int64_t psi_stride, double2 *d_rho, cudaStream_t st)
 {
+    NvtxRange nvtx_range("K1 partial trace (DMMA)");
     const bq::TraceMap *maps = nullptr;
     int rc = get_maps(h, n_qubits, traced, n_traced, n_sets, &maps);
     if (rc) return rc;
@@ -610,6 +612,7 @@ int bq_partial_trace_sv_dev(bq_handle_t h, const double *d_psi, int n_qubits, co
                             int batch, int64_t psi_stride, double *d_rho_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_partial_trace_sv_dev");
     int rc = check_trace_args(d_psi, n_qubits, n_traced, batch, psi_stride, d_rho_out);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(h->mu);
@@ -624,6 +627,7 @@ int bq_partial_trace_sv_multi_dev(bq_handle_t h, const double *d_psi, int n_qubi
                                   int n_traced, int n_sets, double *d_rho_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_partial_trace_sv_multi_dev");
     int rc = check_trace_args(d_psi, n_qubits, n_traced, 1, 0, d_rho_out);
     if (rc) return rc;
     if (n_sets < 0 || n_sets > 4096) return fail(BQ_ERR_INVALID, "n_sets out of range [0, 4096]");
@@ -682,6 +686,7 @@ int bq_partial_trace_sv_multi_host(bq_handle_t h, const double *psi, int n_qubit
 static int trace_accumulate_core(bq_handle_t h, const double2 *d_psi, int n_qubits, const int *traced, int n_traced, int shots,
                                  int64_t psi_stride, const double *d_weights, double2 *d_rho, cudaStream_t st)
 {
+    NvtxRange nvtx_range("K1 partial trace, shot average");
     const bq::TraceMap *maps = nullptr;
     int rc = get_maps(h, n_qubits, traced, n_traced, 1, &maps);
     if (rc) return rc;
@@ -743,6 +748,7 @@ int bq_partial_trace_sv_accumulate_host(bq_handle_t h, const double *psi, int n_
 static int trace_dm_core(bq_handle_t h, const double2 *d_rho, int n_qubits, const int *traced, int n_traced, int batch,
                          double2 *d_out, cudaStream_t st)
 {
+    NvtxRange nvtx_range("K2 partial trace of a density matrix");
     const bq::TraceMap *maps = nullptr;
     int rc = get_maps(h, n_qubits, traced, n_traced, 1, &maps);
     if (rc) return rc;
@@ -766,6 +772,7 @@ int bq_partial_trace_dm_dev(bq_handle_t h, const double *d_rho, int n_qubits, co
                             int batch, double *d_rho_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_partial_trace_dm_dev");
     int rc = check_dm_args(d_rho, n_qubits, n_traced, batch, d_rho_out);
     if (rc) return rc;
     if (batch == 0) return BQ_OK;
@@ -780,6 +787,7 @@ int bq_partial_trace_dm_host(bq_handle_t h, const double *rho, int n_qubits, con
                              int batch, double *rho_out)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_partial_trace_dm_host");
     int rc = check_dm_args(rho, n_qubits, n_traced, batch, rho_out);
     if (rc) return rc;
     if (batch == 0) return BQ_OK;
@@ -802,6 +810,7 @@ int bq_partial_trace_dm_host(bq_handle_t h, const double *rho, int n_qubits, con
 int bq_photon_number_dev(bq_handle_t h, const double *d_rho, int D, int batch, double *d_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_photon_number_dev");
     if (D < 1 || batch < 0) return fail(BQ_ERR_INVALID, "bad size");
     if (batch == 0) return BQ_OK;
     if (!d_rho || !d_out) return fail(BQ_ERR_INVALID, "NULL pointer");
@@ -820,6 +829,7 @@ int bq_photon_number_dev(bq_handle_t h, const double *d_rho, int D, int batch, d
 int bq_photon_number_host(bq_handle_t h, const double *rho, int D, int batch, double *out)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_photon_number_host");
     if (D < 1 || batch < 0) return fail(BQ_ERR_INVALID, "bad size");
     if (batch == 0) return BQ_OK;
     if (!rho || !out) return fail(BQ_ERR_INVALID, "NULL pointer");
@@ -847,6 +857,7 @@ int bq_wigner_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int64_t
                   double *d_W_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_wigner_dev");
     int rc = check_method(method);
     if (rc) return rc;
     if ((rc = check_wigner_args(d_rho, N, ld, rho_stride, batch, d_xvec, nx, d_yvec, ny, g, d_W_out))) return rc;
@@ -862,6 +873,7 @@ int bq_wigner_host(bq_handle_t h, const double *rho, int N, int64_t ld, int64_t 
                    const double *xvec, int nx, const double *yvec, int ny, double g, int method, double *W_out)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_wigner_host");
     int rc = check_method(method);
     if (rc) return rc;
     if ((rc = check_wigner_args(rho, N, ld, rho_stride, batch, xvec, nx, yvec, ny, g, W_out))) return rc;
@@ -911,6 +923,7 @@ int fft_axis(const double *xvec, int nx, double g, double *yvec_out, double *sca
 int wigner_fft_core(bq_handle_t h, const double2 *d_rho, int N, int64_t ld, int64_t rho_stride, int batch,
                     const double *xvec, int nx, double g, double *d_W, double *yvec_out, cudaStream_t st)
 {
+    NvtxRange nvtx_range("K6 wigner method=fft");
     if (N < 1 || N > 16384) return fail(BQ_ERR_INVALID, "cutoff N out of range [1, 16384]");
     if (batch < 0) return fail(BQ_ERR_INVALID, "negative size");
     if (nx < 2) return fail(BQ_ERR_INVALID, "method='fft' needs at least two grid points (the p axis comes from xvec[1] - xvec[0])");
@@ -946,6 +959,7 @@ int bq_wigner_fft_dev(bq_handle_t h, const double *d_rho, int N, int64_t ld, int
                       const double *xvec, int nx, double g, double *d_W_out, double *yvec_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_wigner_fft_dev");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard guard(h->dev.device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -958,6 +972,7 @@ int bq_wigner_fft_host(bq_handle_t h, const double *rho, int N, int64_t ld, int6
                        const double *xvec, int nx, double g, double *W_out, double *yvec_out)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_wigner_fft_host");
     if (N < 1 || ld < N || batch < 0 || nx < 0) return fail(BQ_ERR_INVALID, "bad size");
     if (batch > 0 && (!rho || !W_out)) return fail(BQ_ERR_INVALID, "NULL pointer");
     if (batch > 1 && rho_stride < 0) return fail(BQ_ERR_INVALID, "negative rho_stride");
@@ -1027,6 +1042,7 @@ int bq_state_to_wigner_dev(bq_handle_t h, const double *d_psi, int n_qubits, con
                            int ny, double g, int method, double *d_W_out, double *d_rho_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_state_to_wigner_dev");
     int rc = check_method(method);
     if (rc) return rc;
     if ((rc = check_trace_args(d_psi, n_qubits, n_traced, batch, psi_stride, d_W_out))) return rc;
@@ -1157,6 +1173,7 @@ int bq_frame_minmax_dev(bq_handle_t h, const double *d_W, int64_t points_per_fra
                         void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_frame_minmax_dev");
     if (points_per_frame < 0 || batch < 0) return fail(BQ_ERR_INVALID, "negative size");
     if (batch == 0) return BQ_OK;
     if (!d_W || !d_out) return fail(BQ_ERR_INVALID, "NULL pointer");
@@ -1217,6 +1234,7 @@ int bq_frame_rgba_dev(bq_handle_t h, const double *d_W, int64_t points_per_frame
                       double zero_abs_max, unsigned char *d_rgba_out, void *stream)
 {
     if (!h) return fail(BQ_ERR_INVALID, "NULL handle");
+    NvtxRange nvtx_call("bq_frame_rgba_dev");
     if (points_per_frame < 0 || batch < 0) return fail(BQ_ERR_INVALID, "negative size");
     if (levels < 2 || levels > 4096) return fail(BQ_ERR_INVALID, "levels out of range [2, 4096]");
     if (batch == 0 || points_per_frame == 0) return BQ_OK;
