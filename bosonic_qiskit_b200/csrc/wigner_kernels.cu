@@ -135,10 +135,9 @@ __device__ __forceinline__ uint64_t pro_deposit(uint64_t v, const int *__restric
 }
 
 // element (i, j), i <= j, of frame `frame` -> its record(s) of the coefficient stream (+ rho_out)
-__device__ __forceinline__ void pro_emit(const WigParams &p, int64_t frame, int i, int j, double re, double im)
+// C: the frame's coefficient stream (global memory, or a CTA's own copy in shared memory); R: the frame's rho or NULL
+__device__ __forceinline__ void pro_emit_to(double2 *C, double2 *R, int N, int i, int j, double re, double im)
 {
-    const int N = p.N;
-    double2 *C = p.cs_w + frame * p.cs_stride;
     const int L = j - i;
     if (L == N - 1) {
         C[0] = make_double2(2.0 * re, 2.0 * im);  // header: 2 rho[0, N-1]
@@ -149,11 +148,15 @@ __device__ __forceinline__ void pro_emit(const WigParams &p, int64_t frame, int 
         C[pos + (K - 1 - i)] = make_double2(f * re, f * im);
         if (i == 0) C[pos + K] = make_double2(0.0, 0.0);  // the diagonal's tail record carries no coefficient
     }
-    if (p.pro_rho_out) {
-        double2 *R = p.pro_rho_out + frame * (int64_t)N * N;
+    if (R) {
         R[(int64_t)i * N + j] = make_double2(re, im);
         if (i != j) R[(int64_t)j * N + i] = make_double2(re, -im);
     }
+}
+
+__device__ __forceinline__ void pro_emit(const WigParams &p, int64_t frame, int i, int j, double re, double im)
+{
+    pro_emit_to(p.cs_w + frame * p.cs_stride, p.pro_rho_out ? p.pro_rho_out + frame * (int64_t)p.N * p.N : nullptr, p.N, i, j, re, im);
 }
 
 // row-by-row index over the upper triangle (row i holds j = i .. N-1) -> (i, j)
@@ -266,6 +269,39 @@ __device__ __noinline__ void fused_prologue(const WigParams &p)
         asm volatile("fence.proxy.async;" ::: "memory");
     }
     __syncthreads();
+}
+
+// pro_mode 3, resident symmetric-grid kernels, tiny traces (fewer than 32 traced indices per element, at most a few thousand
+// products per frame): every CTA builds the coefficient stream of the frame it is about to evaluate ITSELF, straight into its
+// shared memory -- no global stream, no grid-wide barrier (6 us of a 24 us call at cutoff 16 / 200 x 200), no bulk copy per
+// frame.  The trace of a frame is recomputed by every CTA that works on it (a handful: tiles are taken in runs); rho, if asked
+// for, is written by the CTA that holds the frame's first tile.  Same summation order as the grid-wide prologue.
+__device__ __noinline__ void local_prologue(const WigParams &p, int64_t frame, double2 *cs_s, bool write_rho)
+{
+    const int N = p.N, nk = p.pro_n_keep, nt = p.pro_n_trace;
+    const int64_t T = (int64_t)1 << nt, ntri = (int64_t)N * (N + 1) / 2;
+    const int set = (int)(frame / p.pro_psi_batch);
+    const int64_t b = frame - (int64_t)set * p.pro_psi_batch;
+    const TraceMap *map = p.pro_maps + set;
+    const double2 *psi = p.pro_psi + b * p.pro_psi_stride;
+    double2 *R = (write_rho && p.pro_rho_out) ? p.pro_rho_out + frame * (int64_t)N * N : nullptr;
+    uint64_t mask = 0;
+    for (int q = 0; q < nt; ++q) mask |= 1ull << __ldg(map->trace + q);
+    const uint64_t step = pro_deposit(1ull, map->trace, nt);
+    for (int64_t e = threadIdx.x; e < ntri; e += blockDim.x) {
+        int i, j;
+        pro_tri(e, N, i, j);
+        const uint64_t row_i = pro_deposit((uint64_t)i, map->keep, nk), row_j = pro_deposit((uint64_t)j, map->keep, nk);
+        double re = 0.0, im = 0.0;
+        uint64_t toff = 0;
+        for (int64_t t = 0; t < T; ++t) {
+            const double2 x = psi[row_i | toff], y = psi[row_j | toff];
+            re = fma(x.x, y.x, fma(x.y, y.y, re));   // x conj(y)
+            im = fma(x.y, y.x, fma(-x.x, y.y, im));
+            toff = ((toff | ~mask) + step) & mask;
+        }
+        pro_emit_to(cs_s, R, N, i, j, re, im);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -875,7 +911,7 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_sym_resident_kernel(cons
     uint32_t phase = 0;
     int loaded_frame = -1;
     TileCursor tc{0, 0};
-    if (p.pro_mode) fused_prologue(p);
+    if (p.pro_mode && p.pro_mode != 3) fused_prologue(p);
     const int N = p.N;
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
@@ -883,15 +919,28 @@ __global__ void __launch_bounds__(THREADS, MINB) wigner_sym_resident_kernel(cons
         const int tif = tile - frame * p.tiles_per_frame;
         if (frame != loaded_frame) {
             __syncthreads();
-            if (tid == 0) {
-                const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
-                const bool first = loaded_frame < 0;
-                mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
-                if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
-                bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+            const bool first = loaded_frame < 0;
+            if (p.pro_mode == 3) {  // the CTA traces the frame itself, into its own shared memory (local_prologue)
+                if (tid == 0 && first) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)p.R_tot * 32u);
+                    bulk_g2s(tab_s, p.tab, (uint32_t)p.R_tot * 32u, bar);
+                }
+                local_prologue(p, frame, cs_s, tif == 0);
+                __syncthreads();
+                if (first) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                }
+            } else {
+                if (tid == 0) {
+                    const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
+                    mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
+                    if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
+                    bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1u;
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
             loaded_frame = frame;
         }
         SymPoints<CL> s;
@@ -948,22 +997,35 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_resident_mixed_kernel(c
     uint32_t phase = 0;
     int loaded_frame = -1;
     TileCursor tc{0, 0};
-    if (p.pro_mode) fused_prologue(p);
+    if (p.pro_mode && p.pro_mode != 3) fused_prologue(p);
 
     for (int tile = next_tile(p, tc, slot); tile >= 0; tile = next_tile(p, tc, slot)) {
         const int frame = tile / p.tiles_per_frame;
         const int tif = tile - frame * p.tiles_per_frame;
         if (frame != loaded_frame) {
             __syncthreads();
-            if (tid == 0) {
-                const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
-                const bool first = loaded_frame < 0;
-                mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
-                if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
-                bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+            const bool first = loaded_frame < 0;
+            if (p.pro_mode == 3) {  // the CTA traces the frame itself, into its own shared memory (local_prologue)
+                if (tid == 0 && first) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)p.R_tot * 32u);
+                    bulk_g2s(tab_s, p.tab, (uint32_t)p.R_tot * 32u, bar);
+                }
+                local_prologue(p, frame, cs_s, tif == 0);
+                __syncthreads();
+                if (first) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                }
+            } else {
+                if (tid == 0) {
+                    const uint32_t cs_bytes = (uint32_t)p.R_tot * 16u, tab_bytes = (uint32_t)p.R_tot * 32u;
+                    mbar_arrive_expect_tx(bar, cs_bytes + (first ? tab_bytes : 0u));
+                    if (first) bulk_g2s(tab_s, p.tab, tab_bytes, bar);
+                    bulk_g2s(cs_s, p.cs + (int64_t)frame * p.cs_stride, cs_bytes, bar);
+                }
+                mbar_wait(bar, phase);
+                phase ^= 1u;
             }
-            mbar_wait(bar, phase);
-            phase ^= 1u;
             loaded_frame = frame;
         }
         const int64_t base = (int64_t)tif * TILE;
@@ -1704,6 +1766,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 8>, 21, 4, 256, 1.00, 2, 2},
         };
         const bool resident = p.N <= kResidentMaxN;
+        if (p.pro_mode == 3 && !resident) return cudaErrorInvalidValue;  // (the caller only asks for it at resident cutoffs)
         auto smem_of = [&](const SymVariant &v) -> size_t {
             if (resident) return (size_t)p.R_tot * 48 + 64;
             const size_t ring = (size_t)v.stages * (p.N + 1) * 48 + 2 * v.stages * 8 + 64;
@@ -1757,7 +1820,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             q.sym_units = count;
             q.sym_phase = dev.sym_phase;
             q.sym_delay = dev.sym_delay;
-            if (pro_done) q.pro_mode = 0;
+            if (pro_done && q.pro_mode != 3) q.pro_mode = 0;
             pro_done = true;
             const int64_t chunks = v.tile_units ? (count + v.tile_units - 1) / v.tile_units * v.threads : (count + v.cl - 1) / v.cl;
             return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, chunks);

@@ -293,3 +293,25 @@ def test_snapshot_wigners_batched(engine):
     x = np.linspace(-6, 6, 48)
     for k, (_, W) in enumerate(out):
         assert rel_err(W, wigner_clenshaw(partial_trace_sv(psi[k], [3]), x)) < TOL
+
+
+def test_local_prologue_equals_grid_wide_prologue(engine):
+    """Tiny traces at a resident cutoff are done per CTA into shared memory (pro_mode 3); BQ_B200_LOCAL_PROLOGUE=0 keeps the
+    grid-wide prologue: same summation order, bit-identical rho and W."""
+    from bosonic_qiskit_b200 import Engine
+
+    os.environ["BQ_B200_LOCAL_PROLOGUE"] = "0"
+    try:
+        ref_engine = Engine(0)
+    finally:
+        del os.environ["BQ_B200_LOCAL_PROLOGUE"]
+    try:
+        for n_qubits, traced, S, batch in ((5, [4], 200, 1), (5, [0], 33, 3), (6, [1, 4], 48, 2), (7, [6], 130, 8)):
+            psi = random_psi(n_qubits, batch, seed=17 + n_qubits)
+            x = np.linspace(-5, 5, S)
+            W, rho = engine.state_to_wigner(psi, traced, x, return_rho=True)
+            W0, rho0 = ref_engine.state_to_wigner(psi, traced, x, return_rho=True)
+            assert np.array_equal(np.asarray(W), np.asarray(W0)) and np.array_equal(rho, rho0)
+            assert rel_err(W[0], wigner_clenshaw(partial_trace_sv(psi[0], traced), x)) < TOL
+    finally:
+        ref_engine.close()
