@@ -495,7 +495,6 @@ int bq_create(bq_handle_t *out, int device)
         h->dev.sym_force = sv ? std::atoi(sv) : -1;
         if (const char *sp = std::getenv("BQ_B200_SYM_SPLIT")) std::sscanf(sp, "%d:%d", &h->dev.sym_split_main, &h->dev.sym_split_tail);
         if (const char *ph = std::getenv("BQ_B200_SYM_PHASE")) h->dev.sym_phase = std::atoi(ph);
-        if (const char *dl = std::getenv("BQ_B200_SYM_DELAY")) h->dev.sym_delay = std::atoi(dl);
         const char *fu = std::getenv("BQ_B200_FUSED");
         h->fused = !(fu && fu[0] == '0');
         const char *lp = std::getenv("BQ_B200_LOCAL_PROLOGUE");

@@ -33,7 +33,6 @@ struct DeviceInfo {
     int sym_force = -1; // >= 0: tuning aid (env BQ_B200_SYM_VARIANT), only this symmetric-kernel variant is eligible
     int sym_split_main = -1, sym_split_tail = -1;  // tuning aid (env BQ_B200_SYM_SPLIT=main:tail): whole rounds / remainder
     int sym_phase = 1;  // symmetric kernels: stagger the warps of a scheduler (env BQ_B200_SYM_PHASE=0 turns it off)
-    int sym_delay = 0;  // parked ring kernel: warp w starts a tile w * sym_delay cycles late (env BQ_B200_SYM_DELAY)
     int last_variant = -1;  // variant id (kKernelNames index) of the last Wigner kernel launched
     int sass_mode = 1;  // 1: launch the re-scheduled (patched) SASS of the Wigner kernels when the build has it
     uint64_t patched_bad = 0;  // bit v: the patched image of variant v failed the load-time self-check -> nvcc's schedule
@@ -74,7 +73,7 @@ struct WigParams {
     int pro_n_keep, pro_n_trace, pro_psi_batch;
     double2 *pro_rho_out;             // mode 2, optional: [batch][N][N]
     // mirror-symmetric grids (wigner_sym_* kernels): U = ceil(S/2) mirror classes, U(U+1)/2 units per frame
-    int sym, sym_U, sym_phase, sym_delay;
+    int sym, sym_U, sym_phase;
     int64_t sym_units;  // units this launch evaluates per frame ...
     int64_t sym_first;  // ... starting at this unit (a rank's share of one large grid; 0 = the whole grid)
     int64_t sym_want_first, sym_want_count;  // caller's unit range (count < 0: all)

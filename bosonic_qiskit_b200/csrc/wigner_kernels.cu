@@ -1182,14 +1182,6 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(THREADS > 256 ? 168 : TRI
             if (tid == 0) load_group(pg, pK);
             pK = group_end(pK, pg == 0, cap, N);
         }
-        if (p.sym_delay) {
-            // staggered warps: the per-diagonal tails (16 shared-memory accesses of 16 bytes per unit) of the warps of
-            // an SM then fall under each other's DFMA work instead of all meeting at the shared-memory crossbar
-            const long long t0 = clock64(), wait = (long long)(tid >> 5) * p.sym_delay;
-            while (clock64() - t0 < wait) {
-            }
-        }
-
         SymCore<CL> s;
         int ua[CL], ub[CL];
         const int64_t chunk = (int64_t)tif * THREADS + tid;
@@ -1679,7 +1671,6 @@ cudaError_t verify_patched_kernels(DeviceInfo &dev, uint64_t *bad_mask, int *che
                 p.sym_first = 0;
                 p.sym_want_count = -1;
                 p.sym_phase = dev.sym_phase;
-                p.sym_delay = dev.sym_delay;
                 dev.sass_mode = pass;  // 0: nvcc's schedule, 1: the patched image
                 VCHK(cudaMemsetAsync(d_ctr, 0, sizeof(unsigned int) * 4, st));
                 VCHK(cudaMemsetAsync(d_W, 0xFF, sizeof(double) * Wa.size(), st));
@@ -1819,7 +1810,6 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             q.sym_first = first;
             q.sym_units = count;
             q.sym_phase = dev.sym_phase;
-            q.sym_delay = dev.sym_delay;
             if (pro_done && q.pro_mode != 3) q.pro_mode = 0;
             pro_done = true;
             const int64_t chunks = v.tile_units ? (count + v.tile_units - 1) / v.tile_units * v.threads : (count + v.cl - 1) / v.cl;
