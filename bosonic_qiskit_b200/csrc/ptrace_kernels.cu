@@ -75,6 +75,9 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_sv_dmma_kernel(const T
     if (w >= tiles2 * p.splits) return;  // whole warps only
     const int split = (int)(w / tiles2), tile = (int)(w - (int64_t)split * tiles2);
     const int I = tile / p.tiles, J = tile - I * p.tiles;
+    // rho is Hermitian: the blocks below the diagonal are the conjugate transposes of those above it, written by the warp
+    // that owns the upper block (half the FP64 work; rho[j][i] == conj(rho[i][j]) then holds exactly)
+    if (J < I) return;
     const int gi = lane >> 2, kk = lane & 3;
     const int64_t D = (int64_t)1 << p.n_keep, T = (int64_t)1 << p.n_trace;
     uint64_t row_i[MT], row_j[MT];
@@ -131,6 +134,10 @@ __global__ void __launch_bounds__(32 * kTraceWarps) trace_sv_dmma_kernel(const T
             const int64_t col = ((int64_t)J * MT + c) * 8 + kk * 2;
             if (vi[a] && col < D) dst[i * D + col] = make_double2(re0[a][c], im0[a][c]);
             if (vi[a] && col + 1 < D) dst[i * D + col + 1] = make_double2(re1[a][c], im1[a][c]);
+            if (J > I) {
+                if (vi[a] && col < D) dst[col * D + i] = make_double2(re0[a][c], -im0[a][c]);
+                if (vi[a] && col + 1 < D) dst[(col + 1) * D + i] = make_double2(re1[a][c], -im1[a][c]);
+            }
         }
 }
 
