@@ -48,7 +48,7 @@ DFMA_LAT = 8  # cycles between a DFMA and a dependent DFMA in ptxas's own schedu
 GAP = 4  # DFMA slots that cover DFMA_LAT
 LDS_SETTLED = 40  # cycles after which a shared-memory load is taken to have landed (latency ~29 + queueing)
 N_BARRIERS = 6
-UNSUPPORTED = re.compile(r"(@!?U?P\d+\s+)?(BSSY|BSYNC|BAR|SYNCS|WARPSYNC|EXIT|CALL|RET|ST|ATOM|RED|MEMBAR|LDG|LDL|STL|UBLKCP|DMUL|DADD|MUFU)")
+UNSUPPORTED = re.compile(r"(@!?U?P\d+\s+)?(BSSY|BSYNC|BAR|SYNCS|WARPSYNC|EXIT|CALL|RET|ST|ATOM|RED|MEMBAR|LDG|LD\.|LDL|STL|UBLKCP|DMUL|DADD|MUFU)")
 VREG = re.compile(r"(?<![U\w])R(\d+)")
 SRC_SHIFT = (24, 32, 64)
 

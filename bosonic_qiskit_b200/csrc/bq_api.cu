@@ -253,6 +253,19 @@ int wigner_core(bq_handle_t h, const WigSource &src, int N, int batch, const dou
         const int64_t ntri = (int64_t)N * (N + 1) / 2, T = (int64_t)1 << src.n_trace;
         // (few frames only: with hundreds of frames the grid-wide prologue's barrier is noise and recomputing a frame's trace
         // in every CTA that touches it is not -- 512 frames of cutoff 32: 2.97 ms against 3.00 ms)
+        // few kept, many traced indices (per-site reduced density matrices): rows of rho x slices of the traced range
+        if (N <= 16 && T >= 512 && T <= 65536) {
+            // slices of 32 .. 256 traced indices (the slice of Psi has to fit in shared memory next to the kernel's own);
+            // about one (frame, slice) per SM
+            int64_t slices = std::max<int64_t>(1, T / 256);
+            while (slices * 2 * batch <= h->dev.sm_count && T / (slices * 2) >= 32) slices *= 2;
+            const int64_t Tc = T / slices;
+            CU(h->partial.reserve((size_t)batch * ntri * slices * sizeof(double2)));
+            p.pro_mode = 4;
+            p.pro_slices = (int)slices;
+            p.pro_partial = (double2 *)h->partial.ptr;
+            p.pro_smem_bytes = (int)((size_t)N * (Tc + 1) * sizeof(double2) + (size_t)(Tc + N) * sizeof(uint64_t));
+        }
         if (h->local_prologue && mirror_grid && nx == ny && nx >= 2 && N >= 2 && N <= bq::kResidentMaxN && h->unit_count < 0 && T < 32 &&
             ntri * T <= 4096 && batch <= 8)
             p.pro_mode = 3;
@@ -1010,6 +1023,7 @@ static bool trace_fits_prologue(const bq_handle_t h, int n_keep, int n_traced, i
 {
     if (!h->fused || n_keep > 12) return false;
     const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_traced;
+    if (D <= 16 && T >= 512 && T <= 65536 && frames <= 256) return true;  // slices of Psi through shared memory (pro_mode 4)
     const int64_t items = frames * (D * (D + 1) / 2);
     // serial length of the prologue per warp (thread) on a conservatively small grid of 512 warps
     const int64_t est = T < 32 ? ((items + 16383) / 16384) * T : ((items + 511) / 512) * (T / 32);

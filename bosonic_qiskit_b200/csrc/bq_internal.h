@@ -57,7 +57,7 @@ struct WigParams {
     int N, R_tot, nx, ny, batch;
     int chunks_per_row, tiles_per_frame, total_tiles, grab, vec_ok;
     double g, scale;
-    unsigned int *ctr;  // [0] next tile, [1] CTAs that left, [2] CTAs that finished the fused prologue
+    unsigned int *ctr;  // [0] next tile, [1] CTAs that left, [2] CTAs that finished the fused prologue, [3] ... its first pass
     // Fused prologue (one launch per step instead of trace + split reduce + pack + Wigner): before any tile is
     // started the CTAs of the launch build the coefficient stream `cs` themselves -- from rho (pro_mode 1, what
     // pack_rho_kernel does) or straight from the statevectors (pro_mode 2: the partial trace rho = Psi Psi^dagger of
@@ -72,6 +72,11 @@ struct WigParams {
     const TraceMap *pro_maps;
     int pro_n_keep, pro_n_trace, pro_psi_batch;
     double2 *pro_rho_out;             // mode 2, optional: [batch][N][N]
+    // mode 4 (cutoff <= 16 kept, 512 .. 65536 traced indices; resident kernels only): a CTA per (frame, slice of the traced
+    // range), the slice of Psi staged in shared memory behind the kernel's own
+    int pro_slices;                   //         slices of the traced range (a power of two; slice length 32 .. 256)
+    double2 *pro_partial;             //         scratch [batch][N (N + 1) / 2][pro_slices]
+    int pro_smem_bytes, pro_smem_off; //         bytes of shared memory the prologue needs (host) and where they start (launcher)
     // mirror-symmetric grids (wigner_sym_* kernels): U = ceil(S/2) mirror classes, U(U+1)/2 units per frame
     int sym, sym_U, sym_phase;
     int64_t sym_units;  // units this launch evaluates per frame ...

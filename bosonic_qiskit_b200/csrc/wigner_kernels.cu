@@ -112,6 +112,7 @@ __device__ __forceinline__ void leave_grid(const WigParams &p)
             p.ctr[0] = 0u;
             p.ctr[1] = 0u;
             p.ctr[2] = 0u;
+            p.ctr[3] = 0u;
             __threadfence();
         }
     }
@@ -253,6 +254,89 @@ __device__ __noinline__ void fused_prologue(const WigParams &p)
                 }
                 if (lane == 0) pro_emit(p, frame, i, j, re, im);
             }
+        }
+    }
+    else if (p.pro_mode == 4) {
+        // Many traced indices, few kept ones (per-site reduced density matrices of a lattice: cutoff <= 16 kept, thousands
+        // traced).  One warp per element (mode 2) re-reads every amplitude N times from L2 and walks T / 32 serial round
+        // trips: 45 us of a 72 us call at 4 sites x cutoff 16.  Here a CTA takes (frame, slice of the traced range): it
+        // gathers Psi[0 .. N-1, slice] into shared memory ONCE (every load of the gather in flight together), then one
+        // thread per element (i, j >= i) walks the slice out of shared memory.  Partial sums meet in global scratch; a
+        // second pass adds the slices in a fixed order (deterministic) and emits the records.
+        extern __shared__ __align__(128) unsigned char pro_smem_raw[];
+        const int nk = p.pro_n_keep, nt = p.pro_n_trace, S = p.pro_slices;
+        const int Tc = (int)((((int64_t)1 << nt)) / S), ld = Tc + 1;  // (host: S and Tc are powers of two; + 1: rows on distinct banks)
+        double2 *Ps = reinterpret_cast<double2 *>(pro_smem_raw + p.pro_smem_off);      // [N][Tc + 1]
+        uint64_t *dep_t = reinterpret_cast<uint64_t *>(Ps + (size_t)N * ld);           // [Tc] statevector offset of a traced index
+        uint64_t *dep_i = dep_t + Tc;                                                   // [N]  ... of a kept index
+        const int ntri = N * (N + 1) / 2;
+        const int64_t tasks = (int64_t)p.batch * S;
+        for (int64_t task = blockIdx.x; task < tasks; task += gridDim.x) {
+            const int64_t frame = task / S;
+            const int sl = (int)(task - frame * S);
+            const int set = (int)(frame / p.pro_psi_batch);
+            const int64_t b = frame - (int64_t)set * p.pro_psi_batch;
+            const TraceMap *map = p.pro_maps + set;
+            const double2 *psi = p.pro_psi + b * p.pro_psi_stride;
+            __syncthreads();  // the previous task's readers are done
+            for (int t = threadIdx.x; t < Tc + N; t += blockDim.x) {
+                if (t < Tc) dep_t[t] = pro_deposit((uint64_t)(sl * (int64_t)Tc + t), map->trace, nt);
+                else dep_i[t - Tc] = pro_deposit((uint64_t)(t - Tc), map->keep, nk);
+            }
+            __syncthreads();
+            // lanes along the kept index when that is the statevector's lowest bit (contiguous there), else along the slice
+            const bool i_fast = __ldg(map->keep) == 0;
+#pragma unroll 4
+            for (int idx = threadIdx.x; idx < N * Tc; idx += blockDim.x) {
+                const int i = i_fast ? (idx & (N - 1)) : idx / Tc;
+                const int t = i_fast ? (idx >> nk) : (idx & (Tc - 1));
+                Ps[i * ld + t] = psi[dep_i[i] | dep_t[t]];
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < ntri; e += blockDim.x) {
+                int i, j;
+                pro_tri(e, N, i, j);
+                const double2 *xi = Ps + i * ld, *yj = Ps + j * ld;
+                double re[4] = {0.0, 0.0, 0.0, 0.0}, im[4] = {0.0, 0.0, 0.0, 0.0};
+                // (not unrolled further: 16 DFMAs per trip stay below what the build's SASS re-scheduler picks up -- this loop
+                // waits on shared memory, there is nothing to gain and the tool's guarantees are tested on the recurrences)
+#pragma unroll 1
+                for (int t = 0; t < Tc; t += 4) {  // (Tc >= 32)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const double2 x = xi[t + u], y = yj[t + u];
+                        re[u] = fma(x.x, y.x, fma(x.y, y.y, re[u]));   // x conj(y)
+                        im[u] = fma(x.y, y.x, fma(-x.x, y.y, im[u]));
+                    }
+                }
+                p.pro_partial[(frame * ntri + e) * S + sl] = make_double2((re[0] + re[1]) + (re[2] + re[3]), (im[0] + im[1]) + (im[2] + im[3]));
+            }
+        }
+        // every slice written -> add them up
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&p.ctr[3], 1u);
+            unsigned int seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ctr + 3) : "memory");
+                if (seen < gridDim.x) __nanosleep(64);
+            } while (seen < gridDim.x);
+        }
+        __syncthreads();
+        const int64_t gthread = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t q = gthread; q < (int64_t)p.batch * ntri; q += nthreads) {
+            const int64_t frame = q / ntri;
+            int i, j;
+            pro_tri(q - frame * ntri, N, i, j);
+            double re = 0.0, im = 0.0;
+#pragma unroll 8
+            for (int sl = 0; sl < S; ++sl) {
+                const double2 v = __ldcg(p.pro_partial + q * S + sl);
+                re += v.x;
+                im += v.y;
+            }
+            pro_emit(p, frame, i, j, re, im);
         }
     }
     // grid-wide barrier: every CTA of the launch is resident (grid <= occupancy x SMs, see run())
@@ -1813,7 +1897,14 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             if (pro_done && q.pro_mode != 3) q.pro_mode = 0;
             pro_done = true;
             const int64_t chunks = v.tile_units ? (count + v.tile_units - 1) / v.tile_units * v.threads : (count + v.cl - 1) / v.cl;
-            return run(v.plain, v.variant, v.threads, smem_of(v), q, v.cl, dev, st, launches, chunks);
+            size_t smem = smem_of(v);
+            if (q.pro_mode == 4) {  // the prologue's staging area behind the kernel's own shared memory
+                if (!resident) return cudaErrorInvalidValue;
+                smem = (smem + 127) & ~(size_t)127;
+                q.pro_smem_off = (int)smem;
+                smem += (size_t)q.pro_smem_bytes;
+            }
+            return run(v.plain, v.variant, v.threads, smem, q, v.cl, dev, st, launches, chunks);
         };
         // A last round that fills only part of the machine still costs a whole tile.  Tried and measured (tools/
         // sym_split_sweep.py, profiles/r1d_sym_split.txt): whole rounds in one launch and the remainder in a SECOND
@@ -1886,7 +1977,12 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
     }
     if (p.N <= kResidentMaxN) {
         const size_t base = (size_t)p.R_tot * 48 + 64;  // + staging buffer of the tile's bulk store
-        const size_t smem = base + 1024 * sizeof(double);
+        size_t smem = base + 1024 * sizeof(double);
+        if (p.pro_mode == 4) {  // the prologue's staging area behind the kernel's own shared memory
+            smem = (smem + 127) & ~(size_t)127;
+            p.pro_smem_off = (int)smem;
+            smem += (size_t)p.pro_smem_bytes;
+        }
         if (points / (256 * 4) >= 2 * want) {
             // 8 points per thread halve the shared-memory loads per DFMA (same 1024-point tile, 128 threads)
             if (dev.pts8) return run((const void *)wigner_resident_kernel<8, 128, 2>, 5, 128, smem, p, 8, dev, st, launches);

@@ -43,6 +43,13 @@ def test_sass_self_check_passed(engine):
     (10, [3, 4, 5, 6, 7, 8, 9], 56, 1),  # 128 traced indices, cutoff 8
     (7, [], 40, 2),         # nothing traced: rho = |psi><psi| at cutoff 128 (ring kernels)
     (4, [0, 1, 2, 3], 16, 2),  # everything traced: cutoff 1
+    # few kept, >= 512 traced indices: slices of Psi staged in shared memory (pro_mode 4)
+    (13, list(range(9)), 40, 2),            # cutoff 16 kept in the top bits (lanes along the traced slice), 512 traced
+    (13, list(range(4, 13)), 33, 3),        # cutoff 16 kept in the lowest bits (lanes along the kept index)
+    (12, [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11], 24, 2),   # cutoff 2, 2048 traced
+    (14, list(range(2, 13)), 32, 1),        # cutoff 8 from bits 0, 1 and 13; 2048 traced
+    (18, list(range(1, 17)), 24, 1),        # cutoff 4, 65536 traced: the largest this mode takes
+    (19, list(range(1, 18)), 24, 1),        # one more traced bit: back to the separate trace launch
 ])
 def test_fused_trace_vs_oracle(engine, n_qubits, traced, S, batch):
     psi = random_psi(n_qubits, batch, seed=n_qubits * 100 + len(traced))
