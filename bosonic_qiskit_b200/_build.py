@@ -39,6 +39,16 @@ MAX_REGS_FOR = [("wigner_stream_kernelILi4ELi256", 168), ("wigner_stream_kernelI
                 ("wigner_sym_diag_parked_kernelILi4ELi256", 248), ("wigner_sym_diag_parked_kernelILi3ELi384", 168)]
 
 
+# Kernels whose straight-line FP64 blocks (the 8-accumulator tails of the symmetric-grid kernels) are re-scheduled as well:
+# NONE.  The tool can do it (reschedule(block=True): 182 -> 153 issue cycles for the 74 FP64 instructions of the 2-unit tail,
+# bit-identical on hardware, tests/test_sass_resched.py audits it on the real image), but it buys nothing where those blocks
+# matter: 512 frames of cutoff 32 take 2.838 ms with loops AND tails re-scheduled, 2.837 ms with nvcc's own schedule
+# throughout -- at 3 warps per scheduler that kernel waits on latencies (fp64 pipe 72 % busy, `wait` 1.3 per issue), not on
+# register-file ports (profiles/r2d_wigner_sym_resident_c3_metrics.txt).  No gain, so no patched code: set to "wigner_sym_"
+# to try it again.
+BLOCKS_FOR = None
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -91,7 +101,7 @@ def build_patched_image(verbose: bool = False) -> bool:
     else:
         try:
             report = [f"nvcc {release}"] + _sass_resched.patch_file(cubin, patched, min_dfma=20, max_regs=MAX_REGS,
-                                                                    max_regs_for=MAX_REGS_FOR)
+                                                                    max_regs_for=MAX_REGS_FOR, blocks_for=BLOCKS_FOR)
         except Exception as exc:  # the tool refuses rather than guesses; the refusal is in the report, and
             report = [f"re-scheduler failed: {exc!r}"]  # tests/test_sass_resched.py fails on it
             shutil.copyfile(cubin, patched)

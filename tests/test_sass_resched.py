@@ -290,3 +290,152 @@ def test_every_loaded_operand_is_waited_for(images):
                     assert waited, f"{name} {x.addr:#x}: {x.text} reads R{r} of {w.text} with no wait in between"
                     audited += 1
     assert audited > 500
+
+
+# ------------------------------------------------------------------------------------------------ straight-line blocks
+def changed_blocks(orig, patched):
+    for name, io in orig.items():
+        ip = patched[name]
+        loops = set(sr.find_loops(io))
+        for lo, hi in sr.find_blocks(io):
+            if (lo, hi) in loops:
+                continue
+            a, b = io[lo:hi + 1], ip[lo:hi + 1]
+            if any(x.word != y.word for x, y in zip(a, b)):
+                yield name, io, lo, hi, a, b
+
+
+def symbolic_block(body, table):
+    """like symbolic(), with the 32-bit register copies ptxas puts at the end of the accumulator blocks"""
+
+    def vid(key):
+        return table.setdefault(key, len(table))
+
+    regs, loads = {}, 0
+    for x in body:
+        sr.classify(x)
+        m = sr.MOV32.match(x.text)
+        if x.kind == "dfma":
+            args = tuple((slot, regs.get(r, vid(("in", r))), regs.get(r + 1, vid(("in", r + 1)))) for slot, r in x.src)
+            sig = re.sub(r"R\d+(\.reuse)?", "R", x.text)
+            regs[x.dst_base] = vid(("dfma", sig, args, 0))
+            regs[x.dst_base + 1] = vid(("dfma", sig, args, 1))
+        elif x.kind == "lds":
+            for off, r in enumerate(x.dst):
+                regs[r] = vid(("lds", loads, off))
+            loads += 1
+        elif m and m.group(1) is not None:
+            d, s = int(m.group(1)), int(m.group(2))
+            regs[d] = regs.get(s, vid(("in", s)))
+    return regs
+
+
+@pytest.fixture(scope="module")
+def block_images(images, tmp_path_factory):
+    """The build does not re-schedule straight-line blocks (no measured gain, see _build.BLOCKS_FOR); the tool's block mode is
+    exercised here on the real image of the resident symmetric-grid kernels (it handles the accumulator tails of some of them;
+    which ones depends on what ptxas made of the source)."""
+    out = str(tmp_path_factory.mktemp("blocks") / "blocks.cubin")
+    rep = sr.patch_file(ORIG, out, min_dfma=20, max_regs=_build.MAX_REGS, max_regs_for=_build.MAX_REGS_FOR, trials=6,
+                        only="wigner_sym_resident", blocks_for="wigner_sym_")
+    if not any("FP64 issue model" in ln for ln in rep):
+        pytest.skip("this toolchain is not one the re-scheduler patches")
+    assert sum(" block " in ln and "FP64 issue model" in ln for ln in rep) >= 1, rep
+    return images[0], sr.disassemble(out)
+
+
+def test_patched_blocks_are_dataflow_equivalent(block_images):
+    """Straight-line blocks (the accumulator tails): same FP64 operations on the same values, the same copies, and every
+    register that is live when the block is left holds the same expression as in ptxas's code."""
+    images = block_images
+    orig, patched = images
+    checked = 0
+    for name, io, lo, hi, a, b in changed_blocks(*images):
+        checked += 1
+        table = {}
+        ro, rp = symbolic_block(a, table), symbolic_block(b, table)
+        # (the liveness analysis is conservative -- an out-of-line call reads "every" register -- so registers that no
+        # instruction of the kernel names, which is what the tool's spare registers are, are not compared)
+        named = {int(m) + d for x in io for m in sr.VREG.findall(x.text) for d in range(4)}
+        live = sr.live_out_of(io, hi) & named
+        for r in sorted(live & (set(ro) | set(rp))):
+            want = ro.get(r, table.setdefault(("in", r), len(table)))
+            got = rp.get(r, table.setdefault(("in", r), len(table)))
+            assert want == got, f"{name} block {a[0].addr:#x}: R{r} differs"
+
+        def ops(body, kinds):
+            return sorted(re.sub(r"R\d+(\.reuse)?", "R", x.text) if x.kind == "dfma" else x.text for x in body if x.kind in kinds)
+
+        for x in a + b:
+            sr.classify(x)
+        assert ops(a, ("dfma",)) == ops(b, ("dfma",))
+        movs_a = sorted(x.text for x in a if sr.MOV32.match(x.text))
+        movs_b = sorted(x.text for x in b if sr.MOV32.match(x.text))
+        assert movs_a == movs_b
+        for x, y in zip(a, b):
+            if x.kind not in ("dfma", "lds") and not sr.MOV32.match(x.text):
+                assert x.text == y.text
+            assert (x.kind == "dfma") == (y.kind == "dfma") and bool(sr.MOV32.match(x.text)) == bool(sr.MOV32.match(y.text))
+    assert checked >= 1
+
+
+def test_patched_blocks_keep_latencies_and_scoreboards(block_images):
+    """Timing audit of every patched block, from the stall counts of the emitted code: a dependent FP64 instruction issues
+    >= 8 cycles after its producer, a copy >= 11 cycles after the FP64 instruction whose result it copies (ptxas's own
+    minima in this file), nothing overwrites a register before its readers have issued, every operand loaded inside the
+    block is waited for, and every barrier the block waits on without setting it first is waited for by its first instruction
+    (the FP64 instructions' own wait masks are rewritten by the tool)."""
+    images = block_images
+    orig, patched = images
+    audited = 0
+    for name, io, lo, hi, a, b in changed_blocks(*images):
+        for x in a + b:
+            sr.classify(x)
+        t, issue = 0, []
+        for x in b:
+            issue.append(t)
+            t += max(1, x.stall)
+        writer = {}     # register -> (position, kind) of its last writer inside the block
+        last_read = {}  # register -> position of its last reader so far
+        pending = {}    # write barrier index -> positions of loads not yet waited for
+        for k, x in enumerate(b):
+            waits = (x.word >> 116) & 0x3F
+            # shared-memory loads complete in issue order (ptxas's own code relies on it): a wait on a barrier covers
+            # every load issued before the youngest load that set it
+            covered = max((max(v) for bar, v in pending.items() if waits >> bar & 1), default=-1)
+            for bar in list(pending):
+                pending[bar] = [q for q in pending[bar] if q > covered]
+                if not pending[bar]:
+                    del pending[bar]
+            m = sr.MOV32.match(x.text)
+            srcs = [r + d for slot, r in x.src for d in (0, 1)] if x.kind == "dfma" else ([int(m.group(2))] if m and m.group(1) else [])
+            dsts = x.dst if x.kind in ("dfma", "lds") else ([int(m.group(1))] if m and m.group(1) else [])
+            for r in srcs:
+                if r in writer:
+                    kw, kind = writer[r]
+                    if kind == "dfma":
+                        need = 8 if x.kind == "dfma" else 11
+                        assert issue[k] - issue[kw] >= need, f"{name} {x.addr:#x}: {x.text} {issue[k] - issue[kw]} cycles after {b[kw].text}"
+                    elif kind == "lds":
+                        assert not any(kw in v for v in pending.values()), f"{name} {x.addr:#x}: {x.text} reads an unwaited load"
+                    audited += 1
+                last_read[r] = k
+            for r in dsts:
+                # (write after read inside the block: the reader has issued -- position order is enough for in-order issue)
+                writer[r] = (k, "dfma" if x.kind == "dfma" else "lds" if x.kind == "lds" else "mov")
+            if x.kind == "lds":
+                wb = (x.word >> 110) & 7
+                assert wb != 7 or not any(r in [s + d for y in b[k + 1:] if y.kind == "dfma" for slot, s in y.src for d in (0, 1)] for r in x.dst), \
+                    f"{name} {x.addr:#x}: a load whose data the block reads carries no write barrier"
+                if wb != 7:
+                    pending.setdefault(wb, []).append(k)
+        # incoming barriers
+        incoming, set_here = 0, set()
+        for x in a:
+            incoming |= ((x.word >> 116) & 0x3F) & ~sum(1 << s for s in set_here)
+            set_here |= {(x.word >> 110) & 7, (x.word >> 113) & 7} - {7}
+        assert ((b[0].word >> 116) & 0x3F) & incoming == incoming, f"{name} block {a[0].addr:#x}: entry does not drain {incoming:#x}"
+        first = next(k for k, x in enumerate(b) if x.kind == "dfma")
+        last = max(k for k, x in enumerate(b) if x.kind == "dfma")
+        assert issue[first] >= sr.BLOCK_GUARD and t - issue[last] >= sr.BLOCK_GUARD
+    assert audited > 50
