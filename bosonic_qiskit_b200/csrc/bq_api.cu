@@ -98,6 +98,7 @@ struct bq_handle_s {
     int sass_checked = 0;  // kernel variants the load-time SASS self-check compared on this device
     bool fused = true;  // the Wigner launch builds its coefficient stream in its own prologue (BQ_B200_FUSED=0: separate launches)
     bool local_prologue = true;  // tiny traces: per CTA, into shared memory (BQ_B200_LOCAL_PROLOGUE=0: the grid-wide prologue)
+    bool staged_trace = true;    // few kept / many traced indices: slices of psi through shared memory (BQ_B200_STAGED_TRACE=0: a warp per element)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
@@ -254,10 +255,13 @@ int wigner_core(bq_handle_t h, const WigSource &src, int N, int batch, const dou
         // (few frames only: with hundreds of frames the grid-wide prologue's barrier is noise and recomputing a frame's trace
         // in every CTA that touches it is not -- 512 frames of cutoff 32: 2.97 ms against 3.00 ms)
         // few kept, many traced indices (per-site reduced density matrices): rows of rho x slices of the traced range
-        if (N <= 16 && T >= 512 && T <= 65536) {
-            // slices of 32 .. 256 traced indices (the slice of Psi has to fit in shared memory next to the kernel's own);
-            // about one (frame, slice) per SM
-            int64_t slices = std::max<int64_t>(1, T / 256);
+        // (up to 8192 traced indices: beyond, a CTA walks several slices one after the other and the second pass adds
+        // hundreds of partial sums per element -- 4 sites x cutoff 32 (32768 traced): 229 us against 145 us for the DMMA trace
+        // launch + the Wigner launch; 4 sites x cutoff 16 (4096): 50 against 69 us)
+        if (h->staged_trace && N <= 32 && T >= 512 && T <= 8192) {
+            // slices of 32 .. 256 traced indices (128 at cutoff 32: the slice of Psi has to fit in shared memory next to
+            // the kernel's own, <= 66 KB here); about one (frame, slice) per SM
+            int64_t slices = std::max<int64_t>(1, T / (N <= 16 ? 256 : 128));
             while (slices * 2 * batch <= h->dev.sm_count && T / (slices * 2) >= 32) slices *= 2;
             const int64_t Tc = T / slices;
             CU(h->partial.reserve((size_t)batch * ntri * slices * sizeof(double2)));
@@ -512,6 +516,8 @@ int bq_create(bq_handle_t *out, int device)
         h->fused = !(fu && fu[0] == '0');
         const char *lp = std::getenv("BQ_B200_LOCAL_PROLOGUE");
         h->local_prologue = !(lp && lp[0] == '0');
+        const char *stg = std::getenv("BQ_B200_STAGED_TRACE");
+        h->staged_trace = !(stg && stg[0] == '0');
         const char *env = std::getenv("BQ_B200_SASS");
         h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
     }
@@ -1023,7 +1029,7 @@ static bool trace_fits_prologue(const bq_handle_t h, int n_keep, int n_traced, i
 {
     if (!h->fused || n_keep > 12) return false;
     const int64_t D = (int64_t)1 << n_keep, T = (int64_t)1 << n_traced;
-    if (D <= 16 && T >= 512 && T <= 65536 && frames <= 256) return true;  // slices of Psi through shared memory (pro_mode 4)
+    if (h->staged_trace && D <= 32 && T >= 512 && T <= 8192 && frames <= 256) return true;  // slices of Psi through shared memory (pro_mode 4)
     const int64_t items = frames * (D * (D + 1) / 2);
     // serial length of the prologue per warp (thread) on a conservatively small grid of 512 warps
     const int64_t est = T < 32 ? ((items + 16383) / 16384) * T : ((items + 511) / 512) * (T / 32);

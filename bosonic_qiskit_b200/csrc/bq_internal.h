@@ -72,7 +72,7 @@ struct WigParams {
     const TraceMap *pro_maps;
     int pro_n_keep, pro_n_trace, pro_psi_batch;
     double2 *pro_rho_out;             // mode 2, optional: [batch][N][N]
-    // mode 4 (cutoff <= 16 kept, 512 .. 65536 traced indices; resident kernels only): a CTA per (frame, slice of the traced
+    // mode 4 (cutoff <= 32 kept, 512 .. 8192 traced indices; resident kernels only): a CTA per (frame, slice of the traced
     // range), the slice of Psi staged in shared memory behind the kernel's own
     int pro_slices;                   //         slices of the traced range (a power of two; slice length 32 .. 256)
     double2 *pro_partial;             //         scratch [batch][N (N + 1) / 2][pro_slices]

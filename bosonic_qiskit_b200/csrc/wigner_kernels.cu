@@ -257,7 +257,7 @@ __device__ __noinline__ void fused_prologue(const WigParams &p)
         }
     }
     else if (p.pro_mode == 4) {
-        // Many traced indices, few kept ones (per-site reduced density matrices of a lattice: cutoff <= 16 kept, thousands
+        // Many traced indices, few kept ones (per-site reduced density matrices of a lattice: cutoff <= 32 kept, thousands
         // traced).  One warp per element (mode 2) re-reads every amplitude N times from L2 and walks T / 32 serial round
         // trips: 45 us of a 72 us call at 4 sites x cutoff 16.  Here a CTA takes (frame, slice of the traced range): it
         // gathers Psi[0 .. N-1, slice] into shared memory ONCE (every load of the gather in flight together), then one

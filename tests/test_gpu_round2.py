@@ -48,8 +48,9 @@ def test_sass_self_check_passed(engine):
     (13, list(range(4, 13)), 33, 3),        # cutoff 16 kept in the lowest bits (lanes along the kept index)
     (12, [0, 1, 2, 3, 4, 6, 7, 8, 9, 10, 11], 24, 2),   # cutoff 2, 2048 traced
     (14, list(range(2, 13)), 32, 1),        # cutoff 8 from bits 0, 1 and 13; 2048 traced
-    (18, list(range(1, 17)), 24, 1),        # cutoff 4, 65536 traced: the largest this mode takes
-    (19, list(range(1, 18)), 24, 1),        # one more traced bit: back to the separate trace launch
+    (15, list(range(1, 14)), 24, 1),        # cutoff 4, 8192 traced: the largest this mode takes
+    (18, list(range(1, 17)), 24, 1),        # cutoff 4, 65536 traced: the separate trace launch
+    (15, list(range(3, 13)), 40, 2),        # cutoff 32 from bits 0-2 and 13-14, 1024 traced (slices of 128)
 ])
 def test_fused_trace_vs_oracle(engine, n_qubits, traced, S, batch):
     psi = random_psi(n_qubits, batch, seed=n_qubits * 100 + len(traced))

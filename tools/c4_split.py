@@ -12,7 +12,15 @@ import torch  # noqa: E402
 import workloads  # noqa: E402
 from bosonic_qiskit_b200 import get_engine  # noqa: E402
 
-w = workloads.config4()
+# python tools/c4_split.py [sites qubits_per_site grid]   (default: config c4 = 4 sites x 4 qubits, 512 x 512)
+if len(sys.argv) > 3:
+    import numpy as np
+
+    n_sites, nq, S_ = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+    w = dict(psi=workloads.random_state(1 << (n_sites * nq), 0)[None, :], xvec=np.linspace(-6, 6, S_),
+             traced_sets=[[q for q in range(n_sites * nq) if not (nq * j <= q < nq * (j + 1))] for j in range(n_sites)])
+else:
+    w = workloads.config4()
 eng = get_engine(0)
 dev = torch.device("cuda", 0)
 psi = torch.from_numpy(w["psi"][0]).to(dev)
@@ -20,7 +28,8 @@ x = torch.from_numpy(w["xvec"]).to(dev)
 S = x.numel()
 sets = w["traced_sets"]
 out = torch.zeros((len(sets), S, S), dtype=torch.float64, device=dev)
-rho = torch.zeros((len(sets), 16, 16), dtype=torch.complex128, device=dev)
+D = 1 << (psi.numel().bit_length() - 1 - len(sets[0]))
+rho = torch.zeros((len(sets), D, D), dtype=torch.complex128, device=dev)
 eng.state_to_wigner_multi_t(psi, sets, x, out=out, rho_out=rho)
 flush = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
 
@@ -49,7 +58,7 @@ def timed(fn, reps=20):
 
 
 res = {
-    "fused_env": os.environ.get("BQ_B200_FUSED", "1"), "slices": os.environ.get("BQ_B200_PRO_SLICES"), "noflush": os.environ.get("NOFLUSH"),
+    "fused_env": os.environ.get("BQ_B200_FUSED", "1"), "staged": os.environ.get("BQ_B200_STAGED_TRACE", "1"), "slices": os.environ.get("BQ_B200_PRO_SLICES"), "noflush": os.environ.get("NOFLUSH"),
     "wigner_from_rho_us": timed(lambda: eng.wigner_t(rho, x, out=out)),
     "psi_to_wigner_us": timed(lambda: eng.state_to_wigner_multi_t(psi, sets, x, out=out)),
     "kernel": eng.last_wigner_kernel(),
