@@ -690,7 +690,7 @@ def main():
             if lmode == "grid":
                 lmode = "replicas"  # small single-frame legs: every GPU its own copy (weak)
             big = name == "c3"
-            r = b.frames_workload(lw, 5 if big else 20, 3 if big else 10, lmode, pbp_steps=0, want_cpu=False, e2e_steps=3 if big else 20)
+            r = b.frames_workload(lw, 10 if big else 20, 6 if big else 10, lmode, pbp_steps=0, want_cpu=False, e2e_steps=3 if big else 20)
             r["workload"] = WORKLOAD_TEXT[name] + (f", 512 frames over {world} GPU(s)" if name == "c3" else "")
             r["scaling"] = "weak (replicas)" if lmode == "replicas" else ("strong" if world > 1 else "single GPU")
             legs[name] = r
