@@ -298,7 +298,8 @@ def describe(wl: dict, world: int, args) -> dict:
                     "sharding": "replicas: every GPU the whole workload (a single frame cannot be split by frame)"})
     else:
         cfg.update({"frames_per_gpu": frames, "sharding": "none"})
-    cfg["_scaling"] = "weak" if mode == "replicas" else "strong" if world > 1 else "weak"
+    # (the label says how the work per GPU changes with N for this workload, so it is the same at N = 1 as at N = 8)
+    cfg["_scaling"] = "weak" if sharding_mode(wl, max(world, 2), args) == "replicas" else "strong"
     return cfg
 
 
