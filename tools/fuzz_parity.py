@@ -31,7 +31,7 @@ def main():
     rng = np.random.default_rng(args.seed)
     worst = {"wigner": 0.0, "trace": 0.0, "fft": 0.0}
     for case in range(args.cases):
-        kind = rng.choice(["wigner", "wigner", "wigner", "frames", "fft"])
+        kind = rng.choice(["wigner", "wigner", "wigner", "frames", "fft", "sites"])
         N = int(rng.choice([1, 2, 3, 5, 8, 13, 16, 31, 32, 33, 48, 64, 65, 80, 100, 128, 150, 200]))
         S = int(rng.integers(2, 420))
         g = float(rng.choice([np.sqrt(2), 1.0, 2.0, 0.5 + rng.random()]))
@@ -65,6 +65,30 @@ def main():
             ref = np.stack([wigner_clenshaw(r, x, None, g) for r in rho_ref])
             e_r = float(np.abs(rho - rho_ref).max() / np.abs(rho_ref).max())
             err = float(np.abs(np.array(W) - ref).max() / max(np.abs(ref).max(), 1e-300))
+            worst["trace"] = max(worst["trace"], e_r)
+            worst["wigner"] = max(worst["wigner"], err)
+            err = max(err, e_r)
+            N = 1 << nq_mode
+        elif kind == "sites":
+            # few kept, hundreds to thousands of traced indices at random bit positions (the staged trace of the fused
+            # prologue up to 8192 traced indices, the separate trace launch beyond), one or several traces of one state
+            nq_mode = int(rng.integers(1, 6))
+            nq_other = int(rng.integers(8, 15))
+            n = nq_mode + nq_other
+            S = min(S, 96)
+            x = np.linspace(-a, a if mirror else a * (0.3 + 0.6 * rng.random()), S)
+            psi = rng.normal(size=(1 << n)) + 1j * rng.normal(size=(1 << n))
+            psi /= np.linalg.norm(psi)
+            n_sets = int(rng.choice([1, 1, 3]))
+            sets = [sorted(rng.choice(n, size=nq_other, replace=False).tolist()) for _ in range(n_sets)]
+            if n_sets == 1:
+                W, rho = eng.state_to_wigner(psi[None, :], sets[0], x, g=g, return_rho=True)
+            else:
+                W, rho = eng.state_to_wigner_multi(psi, sets, x, g=g, return_rho=True)
+            rho_ref = np.stack([partial_trace_sv(psi, t) for t in sets])
+            ref = np.stack([wigner_clenshaw(r, x, None, g) for r in rho_ref])
+            e_r = float(np.abs(np.array(rho).reshape(rho_ref.shape) - rho_ref).max() / np.abs(rho_ref).max())
+            err = float(np.abs(np.array(W).reshape(ref.shape) - ref).max() / max(np.abs(ref).max(), 1e-300))
             worst["trace"] = max(worst["trace"], e_r)
             worst["wigner"] = max(worst["wigner"], err)
             err = max(err, e_r)
