@@ -1188,7 +1188,15 @@ __global__ void __launch_bounds__(THREADS, 1) wigner_sym_diag_kernel(const WigPa
             }
             const int Kend = group_end(K, g == 0, cap, N);
             for (; K < Kend; ++K) {
-                sym_diagonal<CL>(s, cb + pos, tb + pos, K, sym_lead(p, THREADS));
+                if constexpr (CL == 3 && THREADS == 256) {
+                    // the 3-unit register tile takes eight steps per trip like the parked 4-unit tile (half as many trip
+                    // openings): 9-13 % faster at cutoff 128-1024.  (2 units x 256: +1 % slower, 2 x 384: the 8-step trip does
+                    // not fit its 168 registers re-scheduled; 4 units: no registers to spare -- profiles/r2e_ring_trip8.txt)
+                    const double4 t = sym_diagonal_steps8<CL>(s, cb + pos, tb + pos, K, 2 * sym_lead(p, THREADS));
+                    sym_tail<CL>(s, t);
+                } else {
+                    sym_diagonal<CL>(s, cb + pos, tb + pos, K, sym_lead(p, THREADS));
+                }
                 pos += K + 1;
             }
             __syncwarp();
@@ -1818,6 +1826,17 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             int stages = kDiagStages, parked = 0;  // ring kernels: stages of the ring; Horner accumulators in shared memory
             int tile_units = 0;                     // units per tile when that is not cl * threads (the mixed tile)
         };
+        // Parked 4-unit tile per unit against the register tiles (the 3-unit one = 1.10), measured on 2048^2 / 4096^2 grids
+        // after the 3-unit tile went to eight steps per trip (profiles/r2e_ring_trip8.txt): four / eight steps per trip
+        auto parked_eff = [](int N, bool trip8) {
+            static const double e4[] = {0.984, 1.040, 1.071, 1.138}, e8[] = {1.066, 1.096, 1.115, 1.193};  // N = 128 256 512 1024
+            const double *e = trip8 ? e8 : e4;
+            const double l = std::log2((double)N) - 7.0;
+            if (l <= 0.0) return e[0] + 0.25 * l;  // (below 128 the parking traffic weighs more per step)
+            if (l >= 3.0) return e[3];
+            const int i = (int)l;
+            return e[i] + (e[i + 1] - e[i]) * (l - i);
+        };
         static const SymVariant resident_variants[] = {
             {(const void *)wigner_sym_resident_kernel<3, 128, 2>, 8, 3, 128, 1.00},
             {(const void *)wigner_sym_resident_kernel<2, 192, 2>, 12, 2, 192, 0.92},
@@ -1830,11 +1849,11 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
             {(const void *)wigner_sym_resident_mixed_kernel<4, 3, 256>, 22, 4, 256, 1.04, kDiagStages, 0, 896},
         };
         static const SymVariant ring_variants[] = {
-            {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.00},
-            {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 0.94},
-            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.90},
+            {(const void *)wigner_sym_diag_kernel<3, 256, kDiagStages>, 10, 3, 256, 1.10},  // (eight steps per trip since late round 2)
+            {(const void *)wigner_sym_diag_kernel<2, 384, kDiagStages>, 15, 2, 384, 1.02},
+            {(const void *)wigner_sym_diag_kernel<2, 256, kDiagStages>, 14, 2, 256, 0.95},
             {(const void *)wigner_sym_diag_kernel<1, 256, kDiagStages>, 16, 1, 256, 0.60},
-            {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 18, 4, 256, 0.90},
+            {(const void *)wigner_sym_diag_kernel<4, 256, kDiagStages>, 18, 4, 256, 1.04},
             {(const void *)wigner_sym_diag_parked_kernel<4, 256, 2, 4>, 19, 4, 256, 1.00, 2, 1},
             {(const void *)wigner_sym_diag_parked_kernel<3, 384, 2, 4>, 20, 3, 384, 0.78, 2, 1},
             // eight steps per trip: +0.9 % at cutoff 1024 (369.2 against 372.4 ms on 4096^2), -1 % at cutoff 128
@@ -1876,7 +1895,7 @@ cudaError_t launch_wigner(WigParams p, DeviceInfo &dev, cudaStream_t st, int *la
                 // cutoff <= 32, 0.94 at cutoff 64; the mixed tile 1.02-1.05)
                 const double eff = (resident && v.cl == 2 && v.threads == 128) ? v.eff * (p.N > 32 ? 0.97 : 1.10)
                                    : (resident && v.cl == 2 && p.N > 32) ? v.eff * 0.93
-                                   : v.parked           ? v.eff * (1.10 - 23.0 / p.N) * (v.parked == 2 ? (p.N >= 512 ? 1.009 : 0.99) : 1.0)
+                                   : v.parked           ? v.eff * parked_eff(p.N, v.parked == 2)
                                                         : v.eff;
                 Cand &c = cand[ncand++];
                 c.v = &v;
