@@ -691,7 +691,15 @@ def main():
             if lmode == "grid":
                 lmode = "replicas"  # small single-frame legs: every GPU its own copy (weak)
             big = name == "c3"
-            r = b.frames_workload(lw, 10 if big else 20, 6 if big else 10, lmode, pbp_steps=0, want_cpu=False, e2e_steps=3 if big else 20)
+            leg_sampler = ClockSampler(local) if rank == 0 else None  # (the legs run on a GPU the main workload has heated up)
+            if leg_sampler:
+                leg_sampler.start()
+            try:
+                r = b.frames_workload(lw, 10 if big else 20, 6 if big else 10, lmode, pbp_steps=0, want_cpu=False,
+                                      e2e_steps=3 if big else 20)
+            finally:
+                leg_clocks = leg_sampler.stop() if leg_sampler else None
+            r["clocks"] = leg_clocks
             r["workload"] = WORKLOAD_TEXT[name] + (f", 512 frames over {world} GPU(s)" if name == "c3" else "")
             r["scaling"] = "weak (replicas)" if lmode == "replicas" else ("strong" if world > 1 else "single GPU")
             legs[name] = r
