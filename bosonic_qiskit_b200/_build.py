@@ -39,14 +39,13 @@ MAX_REGS_FOR = [("wigner_stream_kernelILi4ELi256", 168), ("wigner_stream_kernelI
                 ("wigner_sym_diag_parked_kernelILi4ELi256", 248), ("wigner_sym_diag_parked_kernelILi3ELi384", 168)]
 
 
-# Kernels whose straight-line FP64 blocks (the 8-accumulator tails of the symmetric-grid kernels) are re-scheduled as well:
-# NONE.  The tool can do it (reschedule(block=True): 182 -> 153 issue cycles for the 74 FP64 instructions of the 2-unit tail,
-# bit-identical on hardware, tests/test_sass_resched.py audits it on the real image), but it buys nothing where those blocks
-# matter: 512 frames of cutoff 32 take 2.838 ms with loops AND tails re-scheduled, 2.837 ms with nvcc's own schedule
-# throughout -- at 3 warps per scheduler that kernel waits on latencies (fp64 pipe 72 % busy, `wait` 1.3 per issue), not on
-# register-file ports (profiles/r2d_wigner_sym_resident_c3_metrics.txt).  No gain, so no patched code: set to "wigner_sym_"
-# to try it again.
-BLOCKS_FOR = None
+# Kernels whose straight-line FP64 blocks (the 8-accumulator tails of the symmetric-grid kernels) are re-scheduled as well
+# (reschedule(block=True): 182 -> 153 issue cycles for the 74 FP64 instructions of the 2-unit tail): the 2-unit resident
+# tiles.  Same box, same run (tools/sass_ab.sh, profiles/r2f_sass_ab.txt): 512 frames of cutoff 32 take 3.140 ms with nvcc's
+# schedule, 2.967 ms with the loops re-scheduled, 2.833 ms with loops and tails.  Not the mixed 4 + 3 tile: only its 3-unit
+# half is handled and c2 reads 0.1451 against 0.1439 ms with it; the tails of the other kernels the tool refuses (registers,
+# or copies it cannot move).
+BLOCKS_FOR = "wigner_sym_resident_kernelILi2ELi"
 
 
 def _nvcc() -> str:
