@@ -519,7 +519,7 @@ int bq_create(bq_handle_t *out, int device)
         const char *stg = std::getenv("BQ_B200_STAGED_TRACE");
         h->staged_trace = !(stg && stg[0] == '0');
         const char *env = std::getenv("BQ_B200_SASS");
-        h->dev.sass_mode = (env && std::strcmp(env, "plain") == 0) ? 0 : (bq::patched_sass_available() ? 1 : 0);
+        h->dev.sass_mode = (env && (std::strcmp(env, "plain") == 0 || std::strcmp(env, "0") == 0)) ? 0 : (bq::patched_sass_available() ? 1 : 0);
     }
     if (bq::patched_sass_available()) {
         // load-time self-check of the re-scheduled SASS, once per device and process (BQ_B200_SASS_VERIFY=0 skips it)

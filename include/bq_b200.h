@@ -186,7 +186,7 @@ int bq_last_device_ms(bq_handle_t h, double *ms);
 int bq_profile_enable(bq_handle_t h, int on);
 /* Which machine code of the Wigner kernels is launched: mode 1 = the build's re-scheduled SASS (same
  * instructions as nvcc's output, DFMAs re-ordered into operand-reuse chains; the default when the build
- * carries it, overridable with the environment variable BQ_B200_SASS=plain), mode 0 = exactly what nvcc
+ * carries it, overridable with the environment variable BQ_B200_SASS=plain or =0), mode 0 = exactly what nvcc
  * scheduled.  Results are bit-identical.  *active (may be NULL) receives the mode in effect.            */
 int bq_set_sass_mode(bq_handle_t h, int mode, int *active);
 /* Result of the load-time self-check of the re-scheduled SASS: when the first handle on a device is created, every
