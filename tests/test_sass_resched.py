@@ -332,9 +332,9 @@ def symbolic_block(body, table):
 
 @pytest.fixture(scope="module")
 def block_images(images, tmp_path_factory):
-    """The build does not re-schedule straight-line blocks (no measured gain, see _build.BLOCKS_FOR); the tool's block mode is
-    exercised here on the real image of the resident symmetric-grid kernels (it handles the accumulator tails of some of them;
-    which ones depends on what ptxas made of the source)."""
+    """The build re-schedules the straight-line blocks of the kernels _build.BLOCKS_FOR names only (test_blocks_of_the_build_image
+    audits those); here the tool's block mode runs over every resident symmetric-grid kernel of the real image (it handles
+    the accumulator tails of some of them; which ones depends on what ptxas made of the source)."""
     out = str(tmp_path_factory.mktemp("blocks") / "blocks.cubin")
     rep = sr.patch_file(ORIG, out, min_dfma=20, max_regs=_build.MAX_REGS, max_regs_for=_build.MAX_REGS_FOR, trials=6,
                         only="wigner_sym_resident", blocks_for="wigner_sym_")
